@@ -1,0 +1,173 @@
+/* libopenlte_b200.so -- C ABI of the B200-native LTE downlink receive hot path.
+ *
+ * Drop-in boundary for the functions OpenLTE's LTE_fdd_dl_file_scan exercises in liblte_phy
+ * (reference: /root/reference/liblte/hdr/liblte_phy.h, /root/reference/liblte/src/liblte_phy.cc).
+ * Plain pointers and sizes only -- no CUDA, torch or C++ types -- so that any FFI (C++, ctypes, cgo, JNI)
+ * can bind it.  Two families of entry points:
+ *
+ *   lteb200_<stage>_batch(...)   DEVICE pointers, caller's CUDA stream, many subframes / code blocks per call.
+ *                                This is the throughput path (SURVEY.md 8b "what the new library adds").
+ *   lteb200_<stage>(...)         HOST pointers, one unit per call, same argument meaning as the liblte_phy
+ *                                function named beside each declaration.  include/liblte_phy_b200.h wraps
+ *                                these under the reference's own C++ names.
+ *
+ * Conventions shared with the reference: soft bits are LLR-like floats with POSITIVE = bit 0 and the
+ * sentinel 10000.0f = "not received" (liblte_phy.cc:1620); hard bits are one bit per byte; I/Q is two
+ * separate float arrays (re, im) at the host boundary (liblte_phy.h:1170-1177) and interleaved float2
+ * (or int8 pairs, the capture file format) in the batched device API.
+ *
+ * All functions return LTEB200_OK (0) or a negative LTEB200_ERR_*; lteb200_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with LTEB200_ERR_CUDA.
+ */
+#ifndef LTE_B200_H
+#define LTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTEB200_OK            0
+#define LTEB200_ERR_ARGS     (-1)   /* maps to LIBLTE_ERROR_INVALID_INPUTS (liblte_common.h:60-66) */
+#define LTEB200_ERR_CUDA     (-2)
+#define LTEB200_ERR_DECODE   (-3)   /* maps to LIBLTE_ERROR_DECODE_FAIL / INVALID_CRC */
+#define LTEB200_ERR_UNSUPPORTED (-4)
+
+#define LTEB200_RX_NULL_BIT  10000.0f
+
+/* sample-rate index == LIBLTE_PHY_FS_ENUM (liblte_phy.h:196-203) */
+enum { LTEB200_FS_1_92 = 0, LTEB200_FS_3_84, LTEB200_FS_7_68, LTEB200_FS_15_36, LTEB200_FS_30_72 };
+/* == LIBLTE_PHY_MODULATION_TYPE_ENUM (liblte_phy.h:211-216) */
+enum { LTEB200_MOD_BPSK = 0, LTEB200_MOD_QPSK, LTEB200_MOD_16QAM, LTEB200_MOD_64QAM };
+/* turbo decoder selection */
+enum {
+    LTEB200_TURBO_REF_EXACT = 0, /* bit-exact twin of turbo_decode(), liblte_phy.cc:10620-10845 (3 SISO Viterbi passes) */
+    LTEB200_TURBO_MAXLOGMAP = 1  /* n_iter-iteration max-log-MAP (BASELINE.json north_star); no reference counterpart */
+};
+/* I/Q sample formats of the batched API */
+enum { LTEB200_IQ_F32 = 0 /* interleaved float re,im */, LTEB200_IQ_I8 = 1 /* interleaved int8 re,im (capture file) */ };
+
+typedef struct lteb200_ctx lteb200_ctx;
+
+/* ---------------------------------------------------------------------------------------------- context */
+/* Replaces liblte_phy_init / liblte_phy_cleanup (liblte_phy.h:606-612, :638) as far as device state goes:
+ * tables and scratch live in HBM behind this handle.  device < 0 selects the current CUDA device. */
+int         lteb200_create(lteb200_ctx **ctx, int device);
+void        lteb200_destroy(lteb200_ctx *ctx);
+const char *lteb200_last_error(lteb200_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long lteb200_launch_count(lteb200_ctx *ctx);
+const char *lteb200_version(void);
+
+/* ------------------------------------------------------------------------------------------------ turbo */
+/* Batched turbo decode.  d_llr: DEVICE [n_cb][3*(K+4)] floats, interleaved d[3i+x] exactly as
+ * liblte_phy_rate_unmatch_turbo emits and turbo_decode() consumes (liblte_phy.cc:11485, 10662); NOT modified.
+ * d_bits: DEVICE [n_cb][K] bytes, one bit each.  mode: LTEB200_TURBO_*.  n_iter: mode 1 only.
+ * Replaces: turbo_decode(), liblte_phy.cc:10620 (prototype :1530-1535). */
+int lteb200_turbo_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int mode, int n_iter,
+                               uint8_t *d_bits, void *stream);
+/* Host twin of turbo_decode(phy_struct, d_bits, N_d_bits, N_fill_bits, c_bits, N_c_bits): d_bits is modified in
+ * place (sentinels zeroed) like the reference; N_c_bits is left untouched like the reference (H8). */
+int lteb200_turbo_decode(lteb200_ctx *ctx, float *d_bits, uint32_t N_d_bits, uint32_t N_fill_bits, uint8_t *c_bits,
+                         int mode, int n_iter);
+
+/* ---------------------------------------------------------------------------------------- rate unmatching */
+/* Batched liblte_phy_rate_unmatch_turbo (liblte_phy.h:1311-1323, liblte_phy.cc:11246-11490).
+ * d_e: DEVICE [n_cb][e_stride] floats of which the first E are used; d_out: DEVICE [n_cb][3*(K+4)] floats. */
+int lteb200_rate_unmatch_turbo_batch(lteb200_ctx *ctx, const float *d_e, int e_stride, int E, int K, int N_codeblocks,
+                                     int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv_idx, int n_cb,
+                                     float *d_out, void *stream);
+/* Host twin (same argument order as the reference; dummy_bits content is ignored, only N_dummy_bits = K+4 matters). */
+int lteb200_rate_unmatch_turbo(lteb200_ctx *ctx, const float *e_bits, uint32_t N_e_bits, const uint8_t *dummy_bits,
+                               uint32_t N_dummy_bits, uint32_t N_codeblocks, uint32_t tx_mode, uint32_t N_soft,
+                               uint32_t M_dl_harq, int chan_type, uint32_t rv_idx, float *d_bits, uint32_t *N_d_bits);
+
+/* --------------------------------------------------------------------------------- OFDM demod + CRS estimate */
+/* Batched liblte_phy_get_dl_subframe_and_ce (liblte_phy.h:1170-1177, liblte_phy.cc:5905-6200).
+ * d_iq: DEVICE sample stream (format iq_fmt), n_samps complex samples.  Subframe b starts at sample
+ * start_idx[b] (DEVICE int64 array, n_sf entries) and has number subfr_num[b] (DEVICE int32 array).  The stream
+ * must extend 2 OFDM symbols past the last subframe (the estimator reads symbols 14-15, liblte_phy.cc:5946).
+ * d_grid: DEVICE [n_sf][16][12*N_rb_dl] float2 (rx_symb);  d_ce: DEVICE [n_sf][N_ant][14][12*N_rb_dl] float2. */
+int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx,
+                                         int N_rb_dl, int N_id_cell, int N_ant, const long long *d_start_idx,
+                                         const int *d_subfr_num, int n_sf, float *d_grid, float *d_ce, void *stream);
+/* Host twin: arrays laid out as LIBLTE_PHY_SUBFRAME_STRUCT's rx_symb_re/im[16][1200], rx_ce_re/im[4][16][1200]
+ * (liblte_phy.h:226-239).  i_samps/q_samps must hold n_samps floats each. */
+int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps,
+                                   int fs_idx, int N_rb_dl, uint32_t frame_start_idx, uint8_t subfr_num,
+                                   uint32_t N_id_cell, uint8_t N_ant, float *rx_symb_re, float *rx_symb_im,
+                                   float *rx_ce_re, float *rx_ce_im);
+
+/* --------------------------------------------------------------------------------------------- PDSCH receive */
+/* One allocation shape shared by every subframe of a batch (what LIBLTE_PHY_ALLOCATION_STRUCT carries,
+ * liblte_phy.h:684-702, for the fields the receive path reads). */
+typedef struct {
+    int32_t mod_type;        /* LTEB200_MOD_* */
+    int32_t N_prb;
+    int32_t prb[2][110];     /* PRB indices per slot */
+    int32_t tbs;
+    int32_t rv_idx;
+    int32_t tx_mode;
+    int32_t rnti;
+} lteb200_alloc;
+
+/* Batched liblte_phy_pdsch_channel_decode (liblte_phy.h:906-913, liblte_phy.cc:3690-3853) for N_ant == 1 and
+ * single-code-block transport blocks (the envelope in which the reference itself is correct).
+ * For every subframe b and allocation a: RE extraction, ZF, demap, descramble, rate unmatch, turbo decode,
+ * CRC24A.  d_tb_bits: DEVICE [n_sf][n_alloc][tb_stride] bytes (first tbs valid);  d_crc_ok: DEVICE [n_sf][n_alloc]
+ * int32 (1 = CRC24A pass, i.e. the reference would return LIBLTE_SUCCESS). */
+int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell,
+                               int N_ant, const int *d_subfr_num, int n_sf, int N_pdcch_symbs,
+                               const lteb200_alloc *allocs /* HOST */, int n_alloc, int turbo_mode, int n_iter,
+                               uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream);
+/* Host twin of liblte_phy_pdsch_channel_decode for one allocation; returns LTEB200_ERR_DECODE on CRC failure and
+ * leaves out_bits / N_out_bits untouched in that case, like the reference. */
+int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, const float *rx_symb_im,
+                                 const float *rx_ce_re, const float *rx_ce_im, int N_rb_dl, uint32_t subfr_num,
+                                 const lteb200_alloc *alloc, uint32_t N_pdcch_symbs, uint32_t N_id_cell, uint8_t N_ant,
+                                 int turbo_mode, int n_iter, uint8_t *out_bits, uint32_t *N_out_bits);
+
+/* Stage-level device entry points (used by the parity tests and for profiling single kernels). */
+/* soft bits after RE extraction + ZF + demap + descramble: d_soft DEVICE [n_sf][soft_stride] floats (= pdsch_descramb_bits) */
+int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell,
+                              int N_ant, const int *d_subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *alloc,
+                              float *d_soft, int soft_stride, int *n_bits_out /* HOST */, void *stream);
+
+/* --------------------------------------------------------------------------------- whole chain, one call */
+/* I/Q stream -> transport-block bits + CRC verdicts for n_sf subframes (OFDM demod, CE, and PDSCH receive of
+ * every allocation), everything resident in HBM between stages. */
+int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                             int N_id_cell, int N_ant, const long long *d_start_idx, const int *d_subfr_num, int n_sf,
+                             int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
+                             uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream);
+/* Same through HOST buffers (pinned or pageable): copies I/Q in, results out, inside the call. */
+int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                            int N_id_cell, int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf,
+                            int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
+                            uint8_t *h_tb_bits, int tb_stride, int32_t *h_crc_ok);
+
+/* ------------------------------------------------------------------------------------------------- sync */
+/* Host twins of liblte_phy_dl_find_coarse_timing_and_freq_offset (liblte_phy.h:1134-1138, .cc:5697-5852),
+ * liblte_phy_find_pss_and_fine_timing (liblte_phy.h:1068-1075, .cc:5306-5510) and liblte_phy_find_sss
+ * (liblte_phy.h:1106-1113, .cc:5578-5686).  Outputs have the reference's meaning. */
+int lteb200_find_coarse_timing_and_freq_offset(lteb200_ctx *ctx, const float *i_samps, const float *q_samps,
+                                               long long n_samps, int fs_idx, uint32_t N_slots, float *freq_offset /*[5]*/,
+                                               uint32_t *symb_starts /*[5][7]*/, uint32_t *n_corr_peaks);
+int lteb200_find_pss_and_fine_timing(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps,
+                                     int fs_idx, int N_rb_dl, uint32_t *symb_starts /*[7] in/out*/, uint32_t *N_id_2,
+                                     uint32_t *pss_symb, float *pss_thresh, float *freq_offset);
+int lteb200_find_sss(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps, int fs_idx,
+                     int N_rb_dl, uint32_t N_id_2, uint32_t *symb_starts /*[7] in/out*/, float pss_thresh,
+                     uint32_t *N_id_1, uint32_t *frame_start_idx);
+
+/* --------------------------------------------------------------------------------------------- utilities */
+/* Pseudo-random sequence c(n), generate_prs_c (liblte_phy.cc:9669-9704); d_c DEVICE [len] bytes. */
+int lteb200_prs_c_batch(lteb200_ctx *ctx, uint32_t c_init, int len, uint8_t *d_c, void *stream);
+/* CRC24A check of n blocks of (tbs+24) bits each (calc_crc, liblte_phy.cc:9713-9743). */
+int lteb200_crc24a_check_batch(lteb200_ctx *ctx, const uint8_t *d_bits, int stride, int tbs, int n, int32_t *d_ok, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTE_B200_H */

@@ -1,0 +1,74 @@
+// Shared host/device plumbing for libopenlte_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lte_b200.h"
+
+#define LTE_CUDA_OK(ctx, call)                                                                      \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            lteb200_set_error((ctx), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return LTEB200_ERR_CUDA;                                                                \
+        }                                                                                           \
+    } while (0)
+
+void lteb200_set_error(lteb200_ctx *ctx, const char *fmt, ...);
+
+// Per-block-size tables of the turbo internal interleaver, resident in HBM.
+struct QppTables {
+    uint16_t *pi;        // [K]  pi(i) with the reference's uint32 wrap (liblte_phy.cc:10982)
+    int16_t  *inv_last;  // [K]  last i with pi(i) == j, or -1 (scatter "last writer wins", liblte_phy.cc:11069)
+};
+
+// Rate-(un)matching gather map for one (K, E, rv, N_cb) configuration.
+struct RateUnmatchMap {
+    int32_t *first_k;    // [3*(K+4)] first e index feeding output d[3i+x], or -1
+    int      n_nonnull;  // period of the circular buffer in e indices
+};
+
+// Per-block-size tables of the max-log-MAP kernel (window-transposed interleaver and its CSR inverse).
+struct MlmTables { uint16_t *piT, *csr_start, *csr_pos; };
+
+struct lteb200_ctx {
+    int          device;
+    std::string  last_error;
+    std::mutex   mu;
+    // growable scratch arena (one arena per context; calls on a context are stream-ordered by the caller)
+    void        *arena;
+    size_t       arena_bytes;
+    std::map<int, QppTables> qpp;
+    std::map<int, MlmTables> mlm;
+    std::map<std::vector<int>, RateUnmatchMap> rum;
+    // statistics
+    unsigned long long launches;
+};
+
+// Returns a device pointer to `bytes` of scratch; grows (synchronously) when needed.
+int lteb200_arena(lteb200_ctx *ctx, size_t bytes, void **ptr);
+
+// Simple bump allocator over the arena.
+struct Bump {
+    char  *base;
+    size_t off;
+    explicit Bump(void *p) : base((char *)p), off(0) {}
+    template <typename T> T *take(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T *r = (T *)(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+
+int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

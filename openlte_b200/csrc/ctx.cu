@@ -1,0 +1,97 @@
+// Context, scratch arena and per-block-size tables.
+#include "common.cuh"
+#include "qpp_table.h"
+#include <stdarg.h>
+
+void lteb200_set_error(lteb200_ctx *ctx, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    else fprintf(stderr, "lteb200: %s\n", buf);
+}
+
+extern "C" const char *lteb200_version(void) { return "openlte_b200 0.1 (sm_100a)"; }
+
+extern "C" int lteb200_create(lteb200_ctx **out, int device)
+{
+    if (!out) return LTEB200_ERR_ARGS;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        lteb200_set_error(nullptr, "no CUDA device (%s): libopenlte_b200 has no CPU fallback",
+                          e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+        return LTEB200_ERR_CUDA;
+    }
+    lteb200_ctx *c = new lteb200_ctx();
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    c->device = device;
+    c->arena = nullptr;
+    c->arena_bytes = 0;
+    c->launches = 0;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
+    *out = c;
+    return LTEB200_OK;
+}
+
+extern "C" void lteb200_destroy(lteb200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->arena) cudaFree(c->arena);
+    for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
+    for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
+    for (auto &kv : c->rum) cudaFree(kv.second.first_k);
+    delete c;
+}
+
+extern "C" const char *lteb200_last_error(lteb200_ctx *c) { return c ? c->last_error.c_str() : "null context"; }
+extern "C" unsigned long long lteb200_launch_count(lteb200_ctx *c) { return c ? c->launches : 0; }
+
+int lteb200_arena(lteb200_ctx *ctx, size_t bytes, void **ptr)
+{
+    if (bytes > ctx->arena_bytes) {
+        // Growing invalidates the old arena: drain outstanding work first.
+        LTE_CUDA_OK(ctx, cudaDeviceSynchronize());
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+        size_t want = bytes + (bytes >> 3) + (1u << 20);
+        LTE_CUDA_OK(ctx, cudaMalloc(&ctx->arena, want));
+        ctx->arena_bytes = want;
+    }
+    *ptr = ctx->arena;
+    return LTEB200_OK;
+}
+
+int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out)
+{
+    auto it = ctx->qpp.find(K);
+    if (it != ctx->qpp.end()) { *out = it->second; return LTEB200_OK; }
+    uint32_t f1 = 0, f2 = 0;
+    bool found = false;
+    for (int r = 0; r < LTE_QPP_TABLE_ROWS; r++)
+        if (LTE_QPP_TABLE[r][0] == K) { f1 = LTE_QPP_TABLE[r][1]; f2 = LTE_QPP_TABLE[r][2]; found = true; break; }
+    if (!found) { lteb200_set_error(ctx, "K=%d is not a turbo block size (36.212 table 5.1.3-3)", K); return LTEB200_ERR_ARGS; }
+    std::vector<uint16_t> pi(K);
+    std::vector<int16_t> inv(K, -1);
+    for (uint32_t i = 0; i < (uint32_t)K; i++) {
+        // uint32 wrap-around is the reference's behaviour (liblte_phy.cc:10982)
+        uint32_t idx = (uint32_t)(f1 * i + f2 * i * i) % (uint32_t)K;
+        pi[i] = (uint16_t)idx;
+        inv[idx] = (int16_t)i;  // increasing i: the last writer wins, as in the sequential scatter
+    }
+    QppTables t;
+    LTE_CUDA_OK(ctx, cudaMalloc(&t.pi, K * sizeof(uint16_t)));
+    LTE_CUDA_OK(ctx, cudaMalloc(&t.inv_last, K * sizeof(int16_t)));
+    LTE_CUDA_OK(ctx, cudaMemcpy(t.pi, pi.data(), K * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    LTE_CUDA_OK(ctx, cudaMemcpy(t.inv_last, inv.data(), K * sizeof(int16_t), cudaMemcpyHostToDevice));
+    ctx->qpp[K] = t;
+    *out = t;
+    return LTEB200_OK;
+}
