@@ -86,12 +86,12 @@ int lteb200_rate_unmatch_turbo(lteb200_ctx *ctx, const float *e_bits, uint32_t N
 /* --------------------------------------------------------------------------------- OFDM demod + CRS estimate */
 /* Batched liblte_phy_get_dl_subframe_and_ce (liblte_phy.h:1170-1177, liblte_phy.cc:5905-6200).
  * d_iq: DEVICE sample stream (format iq_fmt), n_samps complex samples.  Subframe b starts at sample
- * start_idx[b] (DEVICE int64 array, n_sf entries) and has number subfr_num[b] (DEVICE int32 array).  The stream
+ * start_idx[b] (HOST int64 array, n_sf entries) and has number subfr_num[b] (HOST int32 array, 0..9).  The stream
  * must extend 2 OFDM symbols past the last subframe (the estimator reads symbols 14-15, liblte_phy.cc:5946).
  * d_grid: DEVICE [n_sf][16][12*N_rb_dl] float2 (rx_symb);  d_ce: DEVICE [n_sf][N_ant][14][12*N_rb_dl] float2. */
 int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx,
-                                         int N_rb_dl, int N_id_cell, int N_ant, const long long *d_start_idx,
-                                         const int *d_subfr_num, int n_sf, float *d_grid, float *d_ce, void *stream);
+                                         int N_rb_dl, int N_id_cell, int N_ant, const long long *start_idx /* HOST */,
+                                         const int *subfr_num /* HOST */, int n_sf, float *d_grid, float *d_ce, void *stream);
 /* Host twin: arrays laid out as LIBLTE_PHY_SUBFRAME_STRUCT's rx_symb_re/im[16][1200], rx_ce_re/im[4][16][1200]
  * (liblte_phy.h:226-239).  i_samps/q_samps must hold n_samps floats each. */
 int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps,
@@ -118,7 +118,7 @@ typedef struct {
  * CRC24A.  d_tb_bits: DEVICE [n_sf][n_alloc][tb_stride] bytes (first tbs valid);  d_crc_ok: DEVICE [n_sf][n_alloc]
  * int32 (1 = CRC24A pass, i.e. the reference would return LIBLTE_SUCCESS). */
 int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell,
-                               int N_ant, const int *d_subfr_num, int n_sf, int N_pdcch_symbs,
+                               int N_ant, const int *subfr_num /* HOST */, int n_sf, int N_pdcch_symbs,
                                const lteb200_alloc *allocs /* HOST */, int n_alloc, int turbo_mode, int n_iter,
                                uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream);
 /* Host twin of liblte_phy_pdsch_channel_decode for one allocation; returns LTEB200_ERR_DECODE on CRC failure and
@@ -129,16 +129,23 @@ int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, cons
                                  int turbo_mode, int n_iter, uint8_t *out_bits, uint32_t *N_out_bits);
 
 /* Stage-level device entry points (used by the parity tests and for profiling single kernels). */
-/* soft bits after RE extraction + ZF + demap + descramble: d_soft DEVICE [n_sf][soft_stride] floats (= pdsch_descramb_bits) */
+/* samples_to_symbols_dl for 16 symbols per subframe (liblte_phy.cc:8593-8644, called at :5946-5957) */
+int lteb200_ofdm_demod_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                             const long long *start_idx /* HOST */, int n_sf, float *d_grid, void *stream);
+/* the CRS estimator alone (liblte_phy.cc:5959-6193) from a resident grid */
+int lteb200_chan_est_batch(lteb200_ctx *ctx, const float *d_grid, const int *subfr_num /* HOST */, int N_rb_dl, int N_id_cell,
+                           int N_ant, int n_sf, float *d_ce, void *stream);
+/* soft bits after RE extraction + ZF + demap + descramble: d_soft DEVICE [n_sf][soft_stride] floats (= pdsch_descramb_bits);
+ * n_bits_out: HOST [n_sf] number of valid soft bits per subframe (subframes 0 and 5 lose REs to PBCH/PSS/SSS) */
 int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell,
-                              int N_ant, const int *d_subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *alloc,
+                              int N_ant, const int *subfr_num /* HOST */, int n_sf, int N_pdcch_symbs, const lteb200_alloc *alloc,
                               float *d_soft, int soft_stride, int *n_bits_out /* HOST */, void *stream);
 
 /* --------------------------------------------------------------------------------- whole chain, one call */
 /* I/Q stream -> transport-block bits + CRC verdicts for n_sf subframes (OFDM demod, CE, and PDSCH receive of
  * every allocation), everything resident in HBM between stages. */
 int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
-                             int N_id_cell, int N_ant, const long long *d_start_idx, const int *d_subfr_num, int n_sf,
+                             int N_id_cell, int N_ant, const long long *start_idx /* HOST */, const int *subfr_num /* HOST */, int n_sf,
                              int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
                              uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream);
 /* Same through HOST buffers (pinned or pageable): copies I/Q in, results out, inside the call. */

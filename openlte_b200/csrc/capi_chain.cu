@@ -1,0 +1,223 @@
+// C-ABI entry points: OFDM demod + channel estimate, whole-chain receive, host twins.
+#include "internal.h"
+
+int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                      const long long *d_start_idx, int n_sf, float *d_grid, cudaStream_t stream);
+int chan_est_launch(lteb200_ctx *ctx, const float *d_grid, const int *d_subfr_num, int N_rb_dl, int N_id_cell, int N_ant, int n_sf,
+                    float *d_ce, cudaStream_t stream);
+int soa_to_grid(lteb200_ctx *ctx, const float *d_re, const float *d_im, int rows, int nsc, int src_stride, float *d_out, cudaStream_t stream);
+
+namespace {
+__global__ void split_grid_kernel(const float2 *__restrict__ in, int rows, int nsc, int dst_stride, float *__restrict__ re, float *__restrict__ im)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nsc) return;
+    const int r = i / nsc, k = i - r * nsc;
+    const float2 v = in[i];
+    re[r * dst_stride + k] = v.x;
+    im[r * dst_stride + k] = v.y;
+}
+__global__ void interleave_iq_kernel(const float *__restrict__ i_s, const float *__restrict__ q_s, long long n, float2 *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2(i_s[i], q_s[i]);
+}
+}  // namespace
+
+extern "C" int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx,
+                                                    int N_rb_dl, int N_id_cell, int N_ant, const long long *start_idx, const int *subfr_num,
+                                                    int n_sf, float *d_grid, float *d_ce, void *stream_)
+{
+    if (!ctx || !d_iq || !start_idx || !subfr_num || !d_grid || !d_ce || n_sf < 1 || n_samps < 1) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); return LTEB200_ERR_ARGS; }
+    long long *d_start = nullptr;
+    int *d_sn = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_start, start_idx, sizeof(long long) * n_sf, cudaMemcpyHostToDevice, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sn, subfr_num, sizeof(int) * n_sf, cudaMemcpyHostToDevice, stream));
+    int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
+    if (rc == LTEB200_OK) rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
+    cudaFreeAsync(d_start, stream);
+    cudaFreeAsync(d_sn, stream);
+    return rc;
+}
+
+extern "C" int lteb200_ofdm_demod_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                                        const long long *start_idx, int n_sf, float *d_grid, void *stream_)
+{
+    if (!ctx || !d_iq || !start_idx || !d_grid || n_sf < 1) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    long long *d_start = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_start, start_idx, sizeof(long long) * n_sf, cudaMemcpyHostToDevice, stream));
+    int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
+    cudaFreeAsync(d_start, stream);
+    return rc;
+}
+
+extern "C" int lteb200_chan_est_batch(lteb200_ctx *ctx, const float *d_grid, const int *subfr_num, int N_rb_dl, int N_id_cell, int N_ant, int n_sf,
+                                      float *d_ce, void *stream_)
+{
+    if (!ctx || !d_grid || !subfr_num || !d_ce || n_sf < 1 || N_rb_dl < 6 || N_rb_dl > 100) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
+    int *d_sn = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sn, subfr_num, sizeof(int) * n_sf, cudaMemcpyHostToDevice, stream));
+    int rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
+    cudaFreeAsync(d_sn, stream);
+    return rc;
+}
+
+// Host twin of liblte_phy_get_dl_subframe_and_ce (liblte_phy.cc:5905): split float I/Q in, LIBLTE_PHY_SUBFRAME_STRUCT-shaped arrays out.
+extern "C" int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps, int fs_idx,
+                                              int N_rb_dl, uint32_t frame_start_idx, uint8_t subfr_num, uint32_t N_id_cell, uint8_t N_ant,
+                                              float *rx_symb_re, float *rx_symb_im, float *rx_ce_re, float *rx_ce_im)
+{
+    if (!ctx || !i_samps || !q_samps || !rx_symb_re || !rx_symb_im || !rx_ce_re || !rx_ce_im) return LTEB200_ERR_ARGS;
+    if (!(N_ant == 1 || N_ant == 2 || N_ant == 4) || fs_idx < 0 || fs_idx > 4) return LTEB200_ERR_ARGS;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int n_sf_samps = 1920 << fs_idx;
+    const long long start = (long long)frame_start_idx + (long long)subfr_num * n_sf_samps;
+    // only the window [start, start + subframe + 2 symbols + margin) travels to the device
+    const long long lo = start > 0 ? start - 1 : 0;
+    long long hi = start + n_sf_samps + 3LL * ((128 << fs_idx) + (10 << fs_idx));   // symbols 14-15 of the window
+    if (hi > n_samps) hi = n_samps;
+    if (lo >= hi) { lteb200_set_error(ctx, "subframe lies outside the sample buffer"); return LTEB200_ERR_ARGS; }
+    const long long n = hi - lo;
+    const int nsc = 12 * N_rb_dl;
+    float *d_i = nullptr, *d_q = nullptr, *d_iq = nullptr, *d_grid = nullptr, *d_ce = nullptr, *d_soa = nullptr;
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_i, sizeof(float) * n));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_q, sizeof(float) * n));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_iq, sizeof(float) * 2 * n));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_grid, sizeof(float) * 2 * 16 * nsc));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_ce, sizeof(float) * 2 * N_ant * 14 * nsc));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_soa, sizeof(float) * 2 * 4 * 16 * 1200));
+    LTE_CUDA_OK(ctx, cudaMemcpy(d_i, i_samps + lo, sizeof(float) * n, cudaMemcpyHostToDevice));
+    LTE_CUDA_OK(ctx, cudaMemcpy(d_q, q_samps + lo, sizeof(float) * n, cudaMemcpyHostToDevice));
+    interleave_iq_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_i, d_q, n, (float2 *)d_iq);
+    ctx->launches += 1;
+    const long long st = start - lo;
+    const int sn = subfr_num;
+    int rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, LTEB200_IQ_F32, n, fs_idx, N_rb_dl, (int)N_id_cell, N_ant, &st, &sn, 1, d_grid, d_ce, nullptr);
+    if (rc == LTEB200_OK) {
+        float *s_re = d_soa, *s_im = d_soa + 4 * 16 * 1200;
+        cudaMemset(d_soa, 0, sizeof(float) * 2 * 4 * 16 * 1200);
+        split_grid_kernel<<<ceil_div(16 * nsc, 256), 256>>>((const float2 *)d_grid, 16, nsc, 1200, s_re, s_im);
+        cudaMemcpy(rx_symb_re, s_re, sizeof(float) * 16 * 1200, cudaMemcpyDeviceToHost);
+        cudaMemcpy(rx_symb_im, s_im, sizeof(float) * 16 * 1200, cudaMemcpyDeviceToHost);
+        for (int p = 0; p < N_ant; p++)
+            split_grid_kernel<<<ceil_div(14 * nsc, 256), 256>>>((const float2 *)d_ce + (size_t)p * 14 * nsc, 14, nsc, 1200, s_re + p * 16 * 1200, s_im + p * 16 * 1200);
+        ctx->launches += 1 + N_ant;
+        // only rows 0..13 of rx_ce are defined by the reference; rows 14-15 of the caller's arrays are left untouched
+        for (int p = 0; p < N_ant; p++) {
+            cudaMemcpy(rx_ce_re + p * 16 * 1200, s_re + p * 16 * 1200, sizeof(float) * 14 * 1200, cudaMemcpyDeviceToHost);
+            cudaMemcpy(rx_ce_im + p * 16 * 1200, s_im + p * 16 * 1200, sizeof(float) * 14 * 1200, cudaMemcpyDeviceToHost);
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { lteb200_set_error(ctx, "get_dl_subframe_and_ce: %s", cudaGetErrorString(e)); rc = LTEB200_ERR_CUDA; }
+    }
+    cudaFree(d_i); cudaFree(d_q); cudaFree(d_iq); cudaFree(d_grid); cudaFree(d_ce); cudaFree(d_soa);
+    return rc;
+}
+
+// Host twin of liblte_phy_pdsch_channel_decode (liblte_phy.cc:3690) for one allocation.
+extern "C" int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, const float *rx_symb_im, const float *rx_ce_re,
+                                            const float *rx_ce_im, int N_rb_dl, uint32_t subfr_num, const lteb200_alloc *alloc,
+                                            uint32_t N_pdcch_symbs, uint32_t N_id_cell, uint8_t N_ant, int turbo_mode, int n_iter,
+                                            uint8_t *out_bits, uint32_t *N_out_bits)
+{
+    // entry default of the reference: INVALID_INPUTS (liblte_phy.cc:3699-3705)
+    if (!ctx || !rx_symb_re || !rx_symb_im || !rx_ce_re || !rx_ce_im || !alloc || !out_bits || !N_out_bits || N_id_cell > 503) return LTEB200_ERR_ARGS;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int nsc = 12 * N_rb_dl;
+    float *d_in = nullptr, *d_grid = nullptr, *d_ce = nullptr;
+    uint8_t *d_tb = nullptr;
+    int32_t *d_ok = nullptr;
+    const size_t plane = 16 * 1200;
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_in, sizeof(float) * plane * (2 + 2 * N_ant)));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_grid, sizeof(float) * 2 * 16 * nsc));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_ce, sizeof(float) * 2 * N_ant * 14 * nsc));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_tb, alloc->tbs > 0 ? alloc->tbs : 1));
+    LTE_CUDA_OK(ctx, cudaMalloc(&d_ok, sizeof(int32_t)));
+    LTE_CUDA_OK(ctx, cudaMemcpy(d_in, rx_symb_re, sizeof(float) * plane, cudaMemcpyHostToDevice));
+    LTE_CUDA_OK(ctx, cudaMemcpy(d_in + plane, rx_symb_im, sizeof(float) * plane, cudaMemcpyHostToDevice));
+    for (int p = 0; p < N_ant; p++) {
+        LTE_CUDA_OK(ctx, cudaMemcpy(d_in + plane * (2 + 2 * p), rx_ce_re + p * plane, sizeof(float) * plane, cudaMemcpyHostToDevice));
+        LTE_CUDA_OK(ctx, cudaMemcpy(d_in + plane * (3 + 2 * p), rx_ce_im + p * plane, sizeof(float) * plane, cudaMemcpyHostToDevice));
+    }
+    int rc = soa_to_grid(ctx, d_in, d_in + plane, 16, nsc, 1200, d_grid, nullptr);
+    for (int p = 0; p < N_ant && rc == LTEB200_OK; p++)
+        rc = soa_to_grid(ctx, d_in + plane * (2 + 2 * p), d_in + plane * (3 + 2 * p), 14, nsc, 1200, d_ce + (size_t)p * 2 * 14 * nsc, nullptr);
+    const int sn = (int)subfr_num;
+    if (rc == LTEB200_OK)
+        rc = lteb200_pdsch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, (int)N_id_cell, N_ant, &sn, 1, (int)N_pdcch_symbs, alloc, 1, turbo_mode, n_iter,
+                                        d_tb, alloc->tbs, d_ok, nullptr);
+    int32_t ok = 0;
+    if (rc == LTEB200_OK) {
+        cudaError_t e = cudaMemcpy(&ok, d_ok, sizeof(ok), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { lteb200_set_error(ctx, "pdsch_channel_decode: %s", cudaGetErrorString(e)); rc = LTEB200_ERR_CUDA; }
+        else if (!ok) rc = LTEB200_ERR_DECODE;      // demodulated but CRC bad: DECODE_FAIL, outputs untouched (liblte_phy.cc:3720)
+        else {
+            cudaMemcpy(out_bits, d_tb, alloc->tbs, cudaMemcpyDeviceToHost);
+            *N_out_bits = (uint32_t)alloc->tbs;
+        }
+    }
+    cudaFree(d_in); cudaFree(d_grid); cudaFree(d_ce); cudaFree(d_tb); cudaFree(d_ok);
+    return rc;
+}
+
+extern "C" int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                                        int N_id_cell, int N_ant, const long long *start_idx, const int *subfr_num, int n_sf,
+                                        int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
+                                        uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
+{
+    if (!ctx || n_sf < 1) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int nsc = 12 * N_rb_dl;
+    float *d_grid = nullptr, *d_ce = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)n_sf, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)n_sf * N_ant, stream));
+    int rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, start_idx, subfr_num, n_sf, d_grid,
+                                                  d_ce, stream);
+    if (rc == LTEB200_OK)
+        rc = lteb200_pdsch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, subfr_num, n_sf, N_pdcch_symbs, allocs, n_alloc, turbo_mode,
+                                        n_iter, d_tb_bits, tb_stride, d_crc_ok, stream);
+    cudaFreeAsync(d_grid, stream);
+    cudaFreeAsync(d_ce, stream);
+    return rc;
+}
+
+extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl, int N_id_cell,
+                                       int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf, int N_pdcch_symbs,
+                                       const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter, uint8_t *h_tb_bits, int tb_stride,
+                                       int32_t *h_crc_ok)
+{
+    if (!ctx || !h_iq || !h_tb_bits || !h_crc_ok || n_sf < 1 || n_alloc < 1 || n_samps < 1) return LTEB200_ERR_ARGS;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t samp_bytes = iq_fmt == LTEB200_IQ_I8 ? 2 : 8;
+    void *d_iq = nullptr;
+    uint8_t *d_tb = nullptr;
+    int32_t *d_ok = nullptr;
+    cudaStream_t stream = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_iq, samp_bytes * n_samps, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)n_sf * n_alloc * tb_stride, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_iq, h_iq, samp_bytes * n_samps, cudaMemcpyHostToDevice, stream));
+    int rc = lteb200_dl_receive_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx, h_subfr_num, n_sf, N_pdcch_symbs,
+                                      allocs, n_alloc, turbo_mode, n_iter, d_tb, tb_stride, d_ok, stream);
+    if (rc == LTEB200_OK) {
+        cudaMemcpyAsync(h_tb_bits, d_tb, (size_t)n_sf * n_alloc * tb_stride, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(h_crc_ok, d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, cudaMemcpyDeviceToHost, stream);
+    }
+    cudaFreeAsync(d_iq, stream); cudaFreeAsync(d_tb, stream); cudaFreeAsync(d_ok, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (rc == LTEB200_OK && e != cudaSuccess) { lteb200_set_error(ctx, "dl_receive_host: %s", cudaGetErrorString(e)); rc = LTEB200_ERR_CUDA; }
+    return rc;
+}

@@ -2,13 +2,6 @@
 #include "internal.h"
 #define TODO(ctx, name) do { lteb200_set_error(ctx, name " is not implemented yet"); return LTEB200_ERR_UNSUPPORTED; } while (0)
 extern "C" {
-int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void *, int, long long, int, int, int, int, const long long *, const int *, int, float *, float *, void *) { TODO(ctx, "get_dl_subframe_and_ce_batch"); }
-int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *, const float *, long long, int, int, uint32_t, uint8_t, uint32_t, uint8_t, float *, float *, float *, float *) { TODO(ctx, "get_dl_subframe_and_ce"); }
-int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *, const float *, int, int, int, const int *, int, int, const lteb200_alloc *, int, int, int, uint8_t *, int, int32_t *, void *) { TODO(ctx, "pdsch_decode_batch"); }
-int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *, const float *, const float *, const float *, int, uint32_t, const lteb200_alloc *, uint32_t, uint32_t, uint8_t, int, int, uint8_t *, uint32_t *) { TODO(ctx, "pdsch_channel_decode"); }
-int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *, const float *, int, int, int, const int *, int, int, const lteb200_alloc *, float *, int, int *, void *) { TODO(ctx, "pdsch_demod_batch"); }
-int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *, int, long long, int, int, int, int, const long long *, const int *, int, int, const lteb200_alloc *, int, int, int, uint8_t *, int, int32_t *, void *) { TODO(ctx, "dl_receive_batch"); }
-int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *, int, long long, int, int, int, int, const long long *, const int *, int, int, const lteb200_alloc *, int, int, int, uint8_t *, int, int32_t *) { TODO(ctx, "dl_receive_host"); }
 int lteb200_find_coarse_timing_and_freq_offset(lteb200_ctx *ctx, const float *, const float *, long long, int, uint32_t, float *, uint32_t *, uint32_t *) { TODO(ctx, "find_coarse_timing"); }
 int lteb200_find_pss_and_fine_timing(lteb200_ctx *ctx, const float *, const float *, long long, int, int, uint32_t *, uint32_t *, uint32_t *, float *, float *) { TODO(ctx, "find_pss"); }
 int lteb200_find_sss(lteb200_ctx *ctx, const float *, const float *, long long, int, int, uint32_t, uint32_t *, float, uint32_t *, uint32_t *) { TODO(ctx, "find_sss"); }

@@ -1,0 +1,150 @@
+// OFDM demodulation for batches of subframes: CP removal + N-point forward DFT + DC drop / half-spectrum swap.
+// Twin of samples_to_symbols_dl, /root/reference/liblte/src/liblte_phy.cc:8593-8644 (the reference calls FFTW3f
+// there; "any correct unnormalised forward DFT with f32 I/O" is the contract).
+//
+// One CTA per OFDM symbol.  The symbol's N samples (float2, or int8 pairs straight from a capture file) are
+// loaded coalesced into shared memory, transformed by a Stockham autosort FFT (radix-4 passes + one radix-2
+// pass when log2 N is odd) that ping-pongs between two shared buffers, and the 12*N_rb used bins are written
+// coalesced to the resource grid.  Twiddles come from a table computed in double precision on the host.
+// HBM-bound by design: per symbol it reads N*8 B (2 B/sample for int8 input) and writes 12*N_rb*8 B.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+struct OfdmParams {
+    int N, log2N, cp0, cpe, slot;   // FFT size, CP lengths, samples per slot
+    int h;                          // 6*N_rb_dl
+    int nsc;                        // 12*N_rb_dl (grid row length)
+};
+
+template <typename T> __device__ __forceinline__ float2 load_iq(const T *p, long long i);
+template <> __device__ __forceinline__ float2 load_iq<float2>(const float2 *p, long long i) { return p[i]; }
+template <> __device__ __forceinline__ float2 load_iq<char2>(const char2 *p, long long i)
+{
+    const char2 v = p[i];
+    return make_float2((float)v.x, (float)v.y);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+
+// grid: [n_sf][16][nsc] float2.  blockIdx.x = subframe * 16 + symbol.
+template <typename T>
+__global__ void __launch_bounds__(512)
+ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
+                  const float2 *__restrict__ tw /*[N] e^{-2 pi i k/N}*/, float2 *__restrict__ grid)
+{
+    extern __shared__ float2 sm[];
+    float2 *bufA = sm, *bufB = sm + P.N;
+    const int sf = blockIdx.x >> 4, sym = blockIdx.x & 15;
+    const int slot = sym / 7, l = sym % 7;
+    // window start: slot start + (N+CP_else)*l (+CP_0-CP_else for l>0) + CP_l - 1   (one sample early, :8607-8622)
+    long long idx = start_idx[sf] + (long long)slot * P.slot + (long long)(P.N + P.cpe) * l + (l > 0 ? P.cp0 - P.cpe : 0) +
+                    (l == 0 ? P.cp0 : P.cpe) - 1;
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+        const long long s = idx + i;
+        bufA[i] = (s >= 0 && s < n_samps) ? load_iq<T>(iq, s) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    // Stockham autosort, decimation in frequency.  n = remaining transform length, s = stride.
+    float2 *src = bufA, *dst = bufB;
+    int n = P.N, s = 1;
+    while (n > 1) {
+        if ((n & 3) == 0) {
+            const int n1 = n >> 2;
+            for (int t = threadIdx.x; t < (P.N >> 2); t += blockDim.x) {
+                const int p = t / s, q = t - p * s;   // p in [0,n1), q in [0,s)
+                const float2 a = src[q + s * p], b = src[q + s * (p + n1)], c = src[q + s * (p + 2 * n1)], d = src[q + s * (p + 3 * n1)];
+                const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
+                const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
+                const float2 jbmd = make_float2(bmd.y, -bmd.x);  // -j*(b-d) for the forward transform
+                const float2 w1 = tw[p * s], w2 = tw[2 * p * s], w3 = tw[3 * p * s];
+                dst[q + s * (4 * p + 0)] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+                dst[q + s * (4 * p + 1)] = cmul(make_float2(amc.x + jbmd.x, amc.y + jbmd.y), w1);
+                dst[q + s * (4 * p + 2)] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), w2);
+                dst[q + s * (4 * p + 3)] = cmul(make_float2(amc.x - jbmd.x, amc.y - jbmd.y), w3);
+            }
+            n >>= 2; s <<= 2;
+        } else {
+            const int n1 = n >> 1;
+            for (int t = threadIdx.x; t < (P.N >> 1); t += blockDim.x) {
+                const int p = t / s, q = t - p * s;
+                const float2 a = src[q + s * p], b = src[q + s * (p + n1)];
+                dst[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
+                dst[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[p * s]);
+            }
+            n >>= 1; s <<= 1;
+        }
+        __syncthreads();
+        float2 *t_ = src; src = dst; dst = t_;
+    }
+    // bins -> subcarriers (:8625-8634): symb[h+i] = X[i+1], symb[h-1-i] = X[N-1-i]
+    float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
+    for (int k = threadIdx.x; k < 2 * P.h; k += blockDim.x) {
+        const int bin = (k >= P.h) ? (k - P.h + 1) : (P.N - P.h + k);
+        out[k] = src[bin];
+    }
+}
+
+}  // namespace
+
+struct FftTwiddles { float2 *tw; };
+static std::map<std::pair<int, int>, float2 *> g_tw;  // (device, N) -> table
+static std::mutex g_tw_mu;
+
+static int get_twiddles(lteb200_ctx *ctx, int N, float2 **out)
+{
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto key = std::make_pair(ctx->device, N);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) { *out = it->second; return LTEB200_OK; }
+    std::vector<float2> h(N);
+    for (int k = 0; k < N; k++) {
+        const double a = -2.0 * M_PI * (double)k / (double)N;
+        h[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *d = nullptr;
+    LTE_CUDA_OK(ctx, cudaMalloc(&d, sizeof(float2) * N));
+    LTE_CUDA_OK(ctx, cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    g_tw[key] = d;
+    *out = d;
+    return LTEB200_OK;
+}
+
+int fs_legal(int fs_idx, int N_rb_dl)
+{
+    // liblte_phy_update_n_rb_dl, liblte_phy.cc:2601-2641
+    if (fs_idx < 0 || fs_idx > 4) return 0;
+    switch (fs_idx) {
+    case 4: return N_rb_dl >= 1 && N_rb_dl <= 110 && 12 * N_rb_dl < 2048;
+    case 3: return N_rb_dl == 50 || N_rb_dl == 25 || N_rb_dl == 15 || N_rb_dl == 6;
+    case 2: return N_rb_dl == 25 || N_rb_dl == 15 || N_rb_dl == 6;
+    case 1: return N_rb_dl == 15 || N_rb_dl == 6;
+    default: return N_rb_dl == 6;
+    }
+}
+
+int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl,
+                      const long long *d_start_idx, int n_sf, float *d_grid, cudaStream_t stream)
+{
+    if (!fs_legal(fs_idx, N_rb_dl)) { lteb200_set_error(ctx, "illegal (fs, N_rb_dl) = (%d, %d)", fs_idx, N_rb_dl); return LTEB200_ERR_ARGS; }
+    OfdmParams P;
+    P.N = 128 << fs_idx; P.log2N = 7 + fs_idx; P.cp0 = 10 << fs_idx; P.cpe = 9 << fs_idx; P.slot = 960 << fs_idx;
+    P.h = 6 * N_rb_dl; P.nsc = 12 * N_rb_dl;
+    float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, P.N, &tw);
+    if (rc) return rc;
+    const int threads = P.N / 4 < 64 ? 64 : (P.N / 4 > 512 ? 512 : P.N / 4);
+    const size_t smem = sizeof(float2) * 2 * P.N;
+    if (iq_fmt == LTEB200_IQ_F32)
+        ofdm_demod_kernel<float2><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+    else if (iq_fmt == LTEB200_IQ_I8)
+        ofdm_demod_kernel<char2><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+    else { lteb200_set_error(ctx, "unknown I/Q format %d", iq_fmt); return LTEB200_ERR_ARGS; }
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}

@@ -1,0 +1,350 @@
+// PDSCH symbol-level receive for batches of subframes: RE extraction, zero-forcing equaliser, demapping,
+// descrambling, then CRC24A / transport-block extraction after turbo decoding.
+// Twins of (all in /root/reference/liblte/src/liblte_phy.cc):
+//   RE extraction loop of liblte_phy_pdsch_channel_decode   :3745-3802
+//   pre_decoder_and_matched_filter_dl, 1 antenna port (ZF)  :7680-7690
+//   modulation_demapper                                     :9502-9660   (get_soft_decision :13880-13900)
+//   descrambling with generate_prs_c                        :3831-3836, 9669-9704
+//   dlsch_channel_decode tail: desegmentation + CRC24A      :12841-12869, 9713-9743
+//
+// The RE walk depends only on (allocation, cell, subframe class 0 / 5 / other), so it is folded on the host into
+// an index list per class; the kernel is then a fused gather -> ZF -> demap -> descramble, one thread per resource
+// element, reading grid and channel estimate once (8 B + 8 B) and writing Q_m floats: HBM-bound.
+#include "internal.h"
+#include <math.h>
+
+namespace {
+
+struct DemodParams {
+    int nsc;          // 12*N_rb_dl
+    int Qm, mod;
+    int soft_stride;  // floats per subframe in the output
+};
+
+__device__ __forceinline__ float soft_dist(float re, float im, float ere, float eim)
+{
+    // get_soft_decision(rx, exp, max_dist = 1): 1 - min(dist, 1 - 1/120)
+    const float dr = __fsub_rn(re, ere), di = __fsub_rn(im, eim);
+    float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di)));
+    const float lim = __fsub_rn(1.0f, __fdiv_rn(1.0f, 120.0f));
+    if (dist >= lim) dist = lim;
+    return __fsub_rn(1.0f, dist);
+}
+
+// re_idx: [3][idx_stride] (symbol*nsc + subcarrier) per subframe class; M_cls[3]; cseq: [10][c_stride] scrambling bits per subframe number
+__global__ void __launch_bounds__(128)
+pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const float2 *__restrict__ ce /*[n_sf][N_ant][14][nsc]*/, int N_ant,
+                   const int *__restrict__ subfr_num, const int *__restrict__ re_idx, int idx_stride, int3 M_cls,
+                   const uint8_t *__restrict__ cseq, int c_stride, DemodParams P, float *__restrict__ soft)
+{
+    const int sf = blockIdx.y;
+    const int sn = subfr_num[sf];
+    const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
+    const int M = cls == 0 ? M_cls.x : (cls == 1 ? M_cls.y : M_cls.z);
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const int idx = re_idx[cls * idx_stride + r];
+    const float2 y = grid[(size_t)sf * 16 * P.nsc + idx];
+    const float2 h = ce[(size_t)sf * N_ant * 14 * P.nsc + idx];
+    // zero forcing: x = y * conj(h) / |h|^2, operation order of liblte_phy.cc:7684-7689
+    const float nrm = __fadd_rn(__fmul_rn(h.x, h.x), __fmul_rn(h.y, h.y));
+    const float xr = __fdiv_rn(__fadd_rn(__fmul_rn(y.x, h.x), __fmul_rn(y.y, h.y)), nrm);
+    const float xi = __fdiv_rn(__fsub_rn(__fmul_rn(y.y, h.x), __fmul_rn(y.x, h.y)), nrm);
+    int b[6];
+    const float r2 = 0.70710678118654752440f;
+    if (P.mod == LTEB200_MOD_QPSK) {
+        const float ang = atan2f(xi, xr);
+        const double a = (double)ang, hp = 1.57079632679489661923, pi = 3.14159265358979323846;
+        int s0, s1;
+        if (a >= 0 && a < hp) { s0 = 1; s1 = 1; }
+        else if (a >= -hp && a < 0) { s0 = 1; s1 = -1; }
+        else if (a >= hp && a < pi) { s0 = -1; s1 = 1; }
+        else { s0 = -1; s1 = -1; }
+        const int m = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, s0 > 0 ? r2 : -r2, s1 > 0 ? r2 : -r2)));
+        b[0] = s0 * m; b[1] = s1 * m;
+    } else if (P.mod == LTEB200_MOD_16QAM) {
+        const float t = 0.63245553203367586640f;  // 2/sqrt(10)
+        b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
+        b[2] = fabsf(xr) < t ? 127 : -127; b[3] = fabsf(xi) < t ? 127 : -127;
+    } else if (P.mod == LTEB200_MOD_64QAM) {
+        const float t2 = 0.30860669992418382490f, t4 = 0.61721339984836764980f, t6 = 0.92582009977255147470f;  // {2,4,6}/sqrt(42)
+        const float ar = fabsf(xr), ai = fabsf(xi);
+        b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
+        if (ar < t4) { b[2] = 127; b[4] = ar > t2 ? 127 : -127; } else { b[2] = -127; b[4] = ar < t6 ? 127 : -127; }
+        if (ai < t4) { b[3] = 127; b[5] = ai > t2 ? 127 : -127; } else { b[3] = -127; b[5] = ai < t6 ? 127 : -127; }
+    } else {  // BPSK
+        const double a = (double)atan2f(xi, xr), pi = 3.14159265358979323846;
+        if (a > -pi / 4 && a < 3 * pi / 4) b[0] = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, r2, r2)));
+        else b[0] = -__float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, -r2, -r2)));
+    }
+    const uint8_t *c = cseq + (size_t)sn * c_stride + (size_t)r * P.Qm;
+    float *o = soft + (size_t)sf * P.soft_stride + (size_t)r * P.Qm;
+    for (int t = 0; t < P.Qm; t++) o[t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)c[t]));  // soft * (1 - 2c), :3835
+}
+
+// One CTA per code block: CRC24A over the transport block inside the decoded block, bit extraction.
+// cb_bits: [n_cb][K]; F filler bits precede the TB (zero for every legal TBS).
+__global__ void __launch_bounds__(128)
+crc_extract_kernel(const uint8_t *__restrict__ cb_bits, int K, int F, int tbs, int n_sf, int a_idx, int n_alloc,
+                   uint8_t *__restrict__ tb_out, int tb_stride, int32_t *__restrict__ crc_ok)
+{
+    const int sf = blockIdx.x;
+    const uint8_t *a = cb_bits + (size_t)sf * K + F;
+    uint8_t *o = tb_out + ((size_t)sf * n_alloc + a_idx) * tb_stride;
+    for (int i = threadIdx.x; i < tbs; i += blockDim.x) o[i] = a[i];
+    // CRC24A by GF(2) linearity: each warp lane reduces a contiguous chunk, then chunks are combined by
+    // multiplying with x^(bits after the chunk) mod g.  Simple serial form per lane, 32 lanes of warp 0.
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int n = tbs + 24;                    // message followed by its parity: remainder must be 0
+        const int per = (n + 31) / 32;
+        const int beg = lane * per, end = min(n, beg + per);
+        uint32_t rem = 0;
+        for (int i = beg; i < end; i++) {
+            rem = (rem << 1) | (a[i] & 1u);
+            if (rem & 0x1000000u) rem ^= 0x1864CFBu;
+        }
+        // multiply rem by x^(n - end) mod g
+        int sh = n - end;
+        if (sh < 0) sh = 0;
+        for (int i = 0; i < sh; i++) {
+            rem <<= 1;
+            if (rem & 0x1000000u) rem ^= 0x1864CFBu;
+        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o2);
+        if (lane == 0) crc_ok[(size_t)sf * n_alloc + a_idx] = (rem & 0xffffffu) == 0 ? 1 : 0;
+    }
+}
+
+__global__ void soa_to_grid_kernel(const float *__restrict__ re, const float *__restrict__ im, int rows, int nsc, int src_stride,
+                                   float2 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nsc) return;
+    const int r = i / nsc, k = i - r * nsc;
+    out[i] = make_float2(re[r * src_stride + k], im[r * src_stride + k]);
+}
+
+}  // namespace
+
+void centre_band(int N_rb_dl, int *first_sc, int *last_sc)
+{
+    // liblte_phy.cc:3722-3741
+    switch (N_rb_dl) {
+    case 6: *first_sc = 0; *last_sc = 71; break;
+    case 15: *first_sc = 54; *last_sc = 125; break;
+    case 25: *first_sc = 114; *last_sc = 185; break;
+    case 50: *first_sc = 264; *last_sc = 335; break;
+    case 75: *first_sc = 414; *last_sc = 485; break;
+    default: *first_sc = 564; *last_sc = 635; break;
+    }
+}
+
+// RE walk of liblte_phy.cc:3745-3802 for subframe class cls (0: subframe 0, 1: subframe 5, 2: any other)
+static void re_walk(int N_rb_dl, int N_id_cell, int N_ant, int cls, int N_pdcch_symbs, const lteb200_alloc &al, std::vector<int> &idx)
+{
+    int first_sc, last_sc;
+    centre_band(N_rb_dl, &first_sc, &last_sc);
+    const int nsc = 12 * N_rb_dl;
+    idx.clear();
+    for (int L = N_pdcch_symbs; L < 14; L++)
+        for (int pi = 0; pi < al.N_prb; pi++) {
+            const int i = al.prb[L / 7][pi];
+            for (int j = 0; j < 12; j++) {
+                const int sc = 12 * i + j, l7 = L % 7;
+                bool skip;
+                if (N_ant == 1) skip = (l7 == 0 && (N_id_cell % 6) == (j % 6)) || (l7 == 4 && ((N_id_cell + 3) % 6) == (j % 6));
+                else skip = ((l7 == 0 || l7 == 4) && (N_id_cell % 3) == (j % 3)) || (N_ant == 4 && l7 == 1 && (N_id_cell % 3) == (j % 3));
+                const bool centre = sc >= first_sc && sc <= last_sc;
+                if (cls == 0 && centre && L >= 7 && L <= 10) skip = true;
+                if (cls != 2 && centre && (L == 6 || L == 5)) skip = true;
+                if (!skip) idx.push_back(L * nsc + sc);
+            }
+        }
+}
+
+static int seg_params(int tbs, int *K, int *F)
+{
+    // liblte_phy_code_block_segmentation, single code block (liblte_phy.cc:9781-9795)
+    const int B = tbs + 24;
+    if (tbs < 1 || B > 6144) return -1;
+    const int steps[4][3] = {{40, 512, 8}, {528, 1024, 16}, {1056, 2048, 32}, {2112, 6144, 64}};
+    for (int r = 0; r < 4; r++)
+        for (int k = steps[r][0]; k <= steps[r][1]; k += steps[r][2])
+            if (k >= B) { *K = k; *F = k - B; return 0; }
+    return -1;
+}
+
+void prs_c_host(uint32_t c_init, int len, uint8_t *c);
+int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv, RateUnmatchMap *out);
+int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, const int *d_E, int D, const RateUnmatchMap &m, int n_cb,
+                            float *d_out, cudaStream_t stream);
+
+// Per-allocation device tables, cached in the context by content.
+struct AllocTables {
+    int *re_idx;      // [3][idx_stride]
+    int idx_stride;
+    int M[3];
+    uint8_t *cseq;    // [10][c_stride]
+    int c_stride;
+    int Qm, K, F;
+};
+static std::map<std::vector<int>, AllocTables> g_alloc_tabs;
+static std::mutex g_alloc_mu;
+
+static int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc &al, AllocTables *out)
+{
+    if (al.N_prb < 1 || al.N_prb > N_rb_dl || al.mod_type < 0 || al.mod_type > 3) { lteb200_set_error(ctx, "bad allocation"); return LTEB200_ERR_ARGS; }
+    for (int s = 0; s < 2; s++)
+        for (int j = 0; j < al.N_prb; j++)
+            if (al.prb[s][j] < 0 || al.prb[s][j] >= N_rb_dl) { lteb200_set_error(ctx, "PRB index out of range"); return LTEB200_ERR_ARGS; }
+    std::vector<int> key = {ctx->device, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, al.mod_type, al.N_prb, al.rnti, al.tbs};
+    for (int s = 0; s < 2; s++) for (int j = 0; j < al.N_prb; j++) key.push_back(al.prb[s][j]);
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_alloc_tabs.find(key);
+    if (it != g_alloc_tabs.end()) { *out = it->second; return LTEB200_OK; }
+    AllocTables t;
+    const int Qms[4] = {1, 2, 4, 6};
+    t.Qm = Qms[al.mod_type];
+    if (seg_params(al.tbs, &t.K, &t.F)) { lteb200_set_error(ctx, "tbs=%d needs more than one code block: outside the reference's correct envelope (SURVEY H7)", al.tbs); return LTEB200_ERR_UNSUPPORTED; }
+    std::vector<int> idx[3];
+    for (int c = 0; c < 3; c++) { re_walk(N_rb_dl, N_id_cell, N_ant, c, N_pdcch_symbs, al, idx[c]); t.M[c] = (int)idx[c].size(); }
+    t.idx_stride = t.M[2] > 0 ? t.M[2] : 1;   // class 2 (no exclusions) is the largest
+    std::vector<int> flat(3 * (size_t)t.idx_stride, 0);
+    for (int c = 0; c < 3; c++) std::copy(idx[c].begin(), idx[c].end(), flat.begin() + (size_t)c * t.idx_stride);
+    t.c_stride = t.idx_stride * t.Qm;
+    std::vector<uint8_t> cs(10 * (size_t)t.c_stride);
+    for (int sn = 0; sn < 10; sn++)   // c_init = rnti<<14 | q<<13 | subframe<<9 | N_id_cell, liblte_phy.cc:3831
+        prs_c_host(((uint32_t)al.rnti << 14) | ((uint32_t)sn << 9) | (uint32_t)N_id_cell, t.c_stride, cs.data() + (size_t)sn * t.c_stride);
+    LTE_CUDA_OK(ctx, cudaMalloc(&t.re_idx, sizeof(int) * flat.size()));
+    LTE_CUDA_OK(ctx, cudaMalloc(&t.cseq, cs.size()));
+    LTE_CUDA_OK(ctx, cudaMemcpy(t.re_idx, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
+    LTE_CUDA_OK(ctx, cudaMemcpy(t.cseq, cs.data(), cs.size(), cudaMemcpyHostToDevice));
+    g_alloc_tabs[key] = t;
+    *out = t;
+    return LTEB200_OK;
+}
+
+static int upload_ints(lteb200_ctx *ctx, const int *h, int n, int **d_out, cudaStream_t stream)
+{
+    // small per-call parameter arrays: dedicated allocations cached by size class would be overkill here
+    int *d = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d, sizeof(int) * n, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d, h, sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+    *d_out = d;
+    return LTEB200_OK;
+}
+
+int pdsch_demod_launch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
+                       const int *d_subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc &al, float *d_soft, int soft_stride,
+                       AllocTables *tabs_out, cudaStream_t stream)
+{
+    if (N_ant != 1) { lteb200_set_error(ctx, "PDSCH receive: only N_ant == 1 is implemented (transmit diversity combining is a next row)"); return LTEB200_ERR_UNSUPPORTED; }
+    AllocTables t;
+    int rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, al, &t);
+    if (rc) return rc;
+    if (soft_stride < t.M[2] * t.Qm) { lteb200_set_error(ctx, "soft_stride too small: need %d", t.M[2] * t.Qm); return LTEB200_ERR_ARGS; }
+    DemodParams P;
+    P.nsc = 12 * N_rb_dl; P.Qm = t.Qm; P.mod = al.mod_type; P.soft_stride = soft_stride;
+    dim3 grid(ceil_div(t.M[2], 128), n_sf);
+    pdsch_demod_kernel<<<grid, 128, 0, stream>>>((const float2 *)d_grid, (const float2 *)d_ce, N_ant, d_subfr_num, t.re_idx, t.idx_stride,
+                                                 make_int3(t.M[0], t.M[1], t.M[2]), t.cseq, t.c_stride, P, d_soft);
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    if (tabs_out) *tabs_out = t;
+    return LTEB200_OK;
+}
+
+extern "C" int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
+                                         const int *subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *alloc, float *d_soft,
+                                         int soft_stride, int *n_bits_out, void *stream)
+{
+    if (!ctx || !d_grid || !d_ce || !subfr_num || !alloc || !d_soft || n_sf < 1) return LTEB200_ERR_ARGS;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
+    int *d_sn = nullptr;
+    int rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, (cudaStream_t)stream);
+    if (rc) return rc;
+    AllocTables t;
+    rc = pdsch_demod_launch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, d_sn, n_sf, N_pdcch_symbs, *alloc, d_soft, soft_stride, &t, (cudaStream_t)stream);
+    cudaFreeAsync(d_sn, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (n_bits_out) for (int i = 0; i < n_sf; i++) n_bits_out[i] = t.M[subfr_num[i] == 0 ? 0 : (subfr_num[i] == 5 ? 1 : 2)] * t.Qm;
+    return LTEB200_OK;
+}
+
+// Full PDSCH receive of a batch, all allocations.  Scratch layout per allocation a: soft [n_sf][G_stride], d [n_sf][3(K+4)], cb [n_sf][K].
+extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
+                                          const int *subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc,
+                                          int turbo_mode, int n_iter, uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
+{
+    if (!ctx || !d_grid || !d_ce || !subfr_num || !allocs || !d_tb_bits || !d_crc_ok || n_sf < 1 || n_alloc < 1) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); return LTEB200_ERR_ARGS; }
+    std::vector<AllocTables> T(n_alloc);
+    int rc;
+    for (int a = 0; a < n_alloc; a++) {
+        rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[a], &T[a]);
+        if (rc) return rc;
+        if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+    }
+    // per-call device parameter arrays: subframe numbers and per-(alloc, subframe) E
+    std::vector<int> hpar((size_t)n_sf * (1 + n_alloc));
+    for (int i = 0; i < n_sf; i++) hpar[i] = subfr_num[i];
+    for (int a = 0; a < n_alloc; a++)
+        for (int i = 0; i < n_sf; i++)
+            hpar[(size_t)n_sf * (1 + a) + i] = T[a].M[subfr_num[i] == 0 ? 0 : (subfr_num[i] == 5 ? 1 : 2)] * T[a].Qm;
+    int *d_par = nullptr;
+    rc = upload_ints(ctx, hpar.data(), (int)hpar.size(), &d_par, stream);
+    if (rc) return rc;
+    // scratch for the symbol-level stages lives in a stream-ordered allocation (the arena belongs to the turbo decoder)
+    size_t soft_floats = 0, d_floats = 0, cb_bytes = 0;
+    std::vector<size_t> soft_off(n_alloc), d_off(n_alloc), cb_off(n_alloc);
+    for (int a = 0; a < n_alloc; a++) {
+        soft_off[a] = soft_floats; soft_floats += (size_t)n_sf * T[a].c_stride;
+        d_off[a] = d_floats;       d_floats += (size_t)n_sf * 3 * (T[a].K + 4);
+        cb_off[a] = cb_bytes;      cb_bytes += (size_t)n_sf * T[a].K;
+    }
+    float *d_soft = nullptr, *d_d = nullptr;
+    uint8_t *d_cb = nullptr;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_soft, sizeof(float) * soft_floats, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_d, sizeof(float) * d_floats, stream));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_cb, cb_bytes, stream));
+    for (int a = 0; a < n_alloc && rc == LTEB200_OK; a++) {
+        rc = pdsch_demod_launch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, d_par, n_sf, N_pdcch_symbs, allocs[a], d_soft + soft_off[a],
+                                T[a].c_stride, nullptr, stream);
+        if (rc) break;
+        RateUnmatchMap m;
+        rc = rate_unmatch_get_map(ctx, T[a].K + 4, 0, 1, allocs[a].tx_mode, 250368, 8, 0, allocs[a].rv_idx, &m);  // M_dl_harq 8, cat-1 N_soft: liblte_phy.cc:3843-3844
+        if (rc) break;
+        rc = rate_unmatch_launch_var(ctx, d_soft + soft_off[a], T[a].c_stride, d_par + (size_t)n_sf * (1 + a), T[a].K + 4, m, n_sf,
+                                     d_d + d_off[a], stream);
+    }
+    // turbo decode: consecutive allocations with the same K form one batch
+    for (int a = 0; a < n_alloc && rc == LTEB200_OK;) {
+        int e = a + 1;
+        while (e < n_alloc && T[e].K == T[a].K) e++;
+        rc = lteb200_turbo_decode_batch(ctx, d_d + d_off[a], T[a].K, (e - a) * n_sf, turbo_mode, n_iter, d_cb + cb_off[a], stream);
+        a = e;
+    }
+    for (int a = 0; a < n_alloc && rc == LTEB200_OK; a++) {
+        crc_extract_kernel<<<n_sf, 128, 0, stream>>>(d_cb + cb_off[a], T[a].K, T[a].F, allocs[a].tbs, n_sf, a, n_alloc, d_tb_bits, tb_stride, d_crc_ok);
+        ctx->launches += 1;
+    }
+    cudaFreeAsync(d_soft, stream);
+    cudaFreeAsync(d_d, stream);
+    cudaFreeAsync(d_cb, stream);
+    cudaFreeAsync(d_par, stream);
+    if (rc) return rc;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}
+
+int soa_to_grid(lteb200_ctx *ctx, const float *d_re, const float *d_im, int rows, int nsc, int src_stride, float *d_out, cudaStream_t stream)
+{
+    soa_to_grid_kernel<<<ceil_div(rows * nsc, 256), 256, 0, stream>>>(d_re, d_im, rows, nsc, src_stride, (float2 *)d_out);
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}

@@ -34,7 +34,42 @@ rate_unmatch_kernel(const float *__restrict__ e, int e_stride, int E, const int3
     out[(size_t)blockIdx.y * n_out + o] = w;
 }
 
+// Same with a per-code-block number of received bits (subframes 0/5 lose REs to PBCH/PSS/SSS).
+__global__ void __launch_bounds__(256)
+rate_unmatch_var_kernel(const float *__restrict__ e, int e_stride, const int *__restrict__ E_cb, const int32_t *__restrict__ first_k,
+                        int period, int n_out, float *__restrict__ out)
+{
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= n_out) return;
+    const float *eb = e + (size_t)blockIdx.y * e_stride;
+    const int E = E_cb[blockIdx.y];
+    int k = first_k[o];
+    float w = LTEB200_RX_NULL_BIT;
+    if (k >= 0) {
+        for (; k < E; k += period) {
+            const float v = eb[k];
+            if (w == LTEB200_RX_NULL_BIT) w = v;
+            else if (v != LTEB200_RX_NULL_BIT) w = __fadd_rn(w, v);
+        }
+    }
+    out[(size_t)blockIdx.y * n_out + o] = w;
+}
+
 }  // namespace
+
+int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, const int *d_E, int D, const RateUnmatchMap &m, int n_cb,
+                            float *d_out, cudaStream_t stream)
+{
+    for (int base = 0; base < n_cb; base += 32768) {
+        const int n = (n_cb - base) < 32768 ? (n_cb - base) : 32768;
+        dim3 grid(ceil_div(3 * D, 256), n);
+        rate_unmatch_var_kernel<<<grid, 256, 0, stream>>>(d_e + (size_t)base * e_stride, e_stride, d_E + base, m.first_k, m.n_nonnull, 3 * D,
+                                                          d_out + (size_t)base * 3 * D);
+        ctx->launches += 1;
+    }
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}
 
 // Builds (or fetches) the gather map.  Geometry exactly as the reference computes it (liblte_phy.cc:11283-11400).
 int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type,

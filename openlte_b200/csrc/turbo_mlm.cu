@@ -8,7 +8,7 @@
 // restated on the CPU in oracle/port/turbo_mlm.cc (the bit-exact twin the tests compare against).
 //
 // B200 mapping: one CTA per code block, everything of the block resident in shared memory for all iterations
-// (LLRs int8, extrinsics int16, forward metrics of every window int16: 180 KB at K = 6144, so one CTA of
+// (LLRs int8, extrinsics int16, forward metrics of every window int16: 192 KB at K = 6144, so one CTA of
 // 192 threads per SM); one thread per 32-step window holds the 8 forward/backward state metrics in
 // registers (int32, DPX add-max), windows are coupled by state-metric propagation from the previous
 // iteration, so all K/32 windows of a block advance in parallel without warm-up recursions.  Shared-memory
@@ -43,15 +43,20 @@ __device__ __forceinline__ int qf(float v, float maxv)
 
 struct Pass {
     // per-block shared arrays (window-transposed)
-    const int8_t *Lsys;
-    const int16_t *Lapr;
-    const uint16_t *piT;  // nullptr: a-priori read in place; else gathered through piT (global, transposed)
+    const int16_t *Lsa;   // systematic + a-priori LLR, prepared before the pass
     const int8_t *Lp;
     int16_t *LeOut;
     int4 *st;             // [32][nw] packed 8 x int16
     int *bA, *bB;         // [nw][8]
     int xt[3], zt[3];
 };
+
+__device__ __forceinline__ int pack_sat(int lo, int hi)
+{
+    int r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));  // {sat16(hi), sat16(lo)}
+    return r;
+}
 
 __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
 {
@@ -78,7 +83,6 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
                 const Gam G(P.xt[t], P.zt[t]);
 #pragma unroll
                 for (int S = 0; S < 8; S++) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int u = ((S >> 1) & 1) ^ (S & 1);
                     nb[S] = max(G.g[u][tr_par(S, u)] + b[tr_nxt(S, u)], NEG);
                 }
@@ -92,20 +96,20 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
     }
     __syncthreads();  // all boundaries of the previous iteration are read before any is overwritten
 
-    // ---- forward
+    // ---- forward (inputs of step i+1 are fetched while step i computes)
+    int ls_n = 0, lp_n = 0;
+    if (n > 0) { ls_n = P.Lsa[w]; lp_n = P.Lp[w]; }
     for (int i = 0; i < n; i++) {
         const int p = i * nw + w;
-        int4 pk;
+        const int ls = ls_n, lp = lp_n;
+        if (i + 1 < n) { ls_n = P.Lsa[p + nw]; lp_n = P.Lp[p + nw]; }
         {
             const int a0 = a[0];
-            int v[8];
-#pragma unroll
-            for (int s = 0; s < 8; s++) v[s] = clampi(a[s] - a0, -32768, 32767) & 0xffff;
-            pk.x = v[0] | (v[1] << 16); pk.y = v[2] | (v[3] << 16); pk.z = v[4] | (v[5] << 16); pk.w = v[6] | (v[7] << 16);
+            int4 pk;
+            pk.x = pack_sat(0, a[1] - a0); pk.y = pack_sat(a[2] - a0, a[3] - a0);
+            pk.z = pack_sat(a[4] - a0, a[5] - a0); pk.w = pack_sat(a[6] - a0, a[7] - a0);
+            P.st[p] = pk;
         }
-        P.st[p] = pk;
-        const int apr = P.piT ? (int)P.Lapr[P.piT[p]] : (int)P.Lapr[p];
-        const int ls = (int)P.Lsys[p] + apr, lp = (int)P.Lp[p];
         const Gam G(ls, lp);
         int na[8];
 #pragma unroll
@@ -126,17 +130,19 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
         for (int s = 0; s < 8; s++) P.bA[(w + 1) * 8 + s] = max(a[s] - mx, NEG);
     }
     // ---- backward + LLR
+    int4 pk_n = make_int4(0, 0, 0, 0);
+    if (n > 0) { const int p = (n - 1) * nw + w; ls_n = P.Lsa[p]; lp_n = P.Lp[p]; pk_n = P.st[p]; }
     for (int i = n - 1; i >= 0; i--) {
         const int p = i * nw + w;
-        const int apr = P.piT ? (int)P.Lapr[P.piT[p]] : (int)P.Lapr[p];
-        const int ls = (int)P.Lsys[p] + apr, lp = (int)P.Lp[p];
+        const int ls = ls_n, lp = lp_n;
+        const int4 pk = pk_n;
+        if (i > 0) { ls_n = P.Lsa[p - nw]; lp_n = P.Lp[p - nw]; pk_n = P.st[p - nw]; }
         const Gam G(ls, lp);
-        const int4 pk = P.st[p];
         int al[8];
-        al[0] = (int)(int16_t)(pk.x & 0xffff); al[1] = pk.x >> 16;
-        al[2] = (int)(int16_t)(pk.y & 0xffff); al[3] = pk.y >> 16;
-        al[4] = (int)(int16_t)(pk.z & 0xffff); al[5] = pk.z >> 16;
-        al[6] = (int)(int16_t)(pk.w & 0xffff); al[7] = pk.w >> 16;
+        al[0] = (int)(short)(pk.x & 0xffff); al[1] = pk.x >> 16;
+        al[2] = (int)(short)(pk.y & 0xffff); al[3] = pk.y >> 16;
+        al[4] = (int)(short)(pk.z & 0xffff); al[5] = pk.z >> 16;
+        al[6] = (int)(short)(pk.w & 0xffff); al[7] = pk.w >> 16;
         int nb[8], m0 = 0, m1 = 0;
 #pragma unroll
         for (int S = 0; S < 8; S++) {
@@ -173,8 +179,8 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     int4 *st = (int4 *)smem_raw;                                   // 16*NP bytes
     int *bA1 = (int *)(smem_raw + (size_t)16 * NP);                // 4 x nw*8 ints
     int *bB1 = bA1 + nw * 8, *bA2 = bB1 + nw * 8, *bB2 = bA2 + nw * 8;
-    int16_t *La1 = (int16_t *)(bB2 + nw * 8);
-    int16_t *Le1 = La1 + NP, *Le2 = Le1 + NP;
+    int16_t *Lsa1 = (int16_t *)(bB2 + nw * 8);   // Ls + a-priori of decoder 1 (natural order)
+    int16_t *Lsa2 = Lsa1 + NP, *Le1 = Lsa2 + NP, *Le2 = Le1 + NP;
     int8_t *Ls = (int8_t *)(Le2 + NP);
     int8_t *LsI = Ls + NP, *Lp1 = LsI + NP, *Lp2 = Lp1 + NP;
     __shared__ float s_red[32];
@@ -211,7 +217,7 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
             q0 = qf(v0, maxv); q1 = qf(v1, maxv); q2 = qf(v2, maxv);
         }
         Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2;
-        La1[p] = 0; Le1[p] = 0; Le2[p] = 0;
+        Lsa1[p] = (int16_t)q0; Lsa2[p] = 0; Le1[p] = 0; Le2[p] = 0;
     }
     if (tid < 12) {
         float v = d[3 * K + tid];
@@ -224,8 +230,8 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     __syncthreads();
 
     Pass P1, P2;
-    P1.Lsys = Ls; P1.Lapr = La1; P1.piT = nullptr; P1.Lp = Lp1; P1.LeOut = Le1; P1.st = st; P1.bA = bA1; P1.bB = bB1;
-    P2.Lsys = LsI; P2.Lapr = Le1; P2.piT = piT; P2.Lp = Lp2; P2.LeOut = Le2; P2.st = st; P2.bA = bA2; P2.bB = bB2;
+    P1.Lsa = Lsa1; P1.Lp = Lp1; P1.LeOut = Le1; P1.st = st; P1.bA = bA1; P1.bB = bB1;
+    P2.Lsa = Lsa2; P2.Lp = Lp2; P2.LeOut = Le2; P2.st = st; P2.bA = bA2; P2.bB = bB2;
     // tail multiplexing (liblte_phy.cc:10575-10586): x = systematic/feedback bits, z = parity bits of the 3 tail steps
     P1.xt[0] = s_tail[0]; P1.xt[1] = s_tail[2]; P1.xt[2] = s_tail[4];
     P1.zt[0] = s_tail[1]; P1.zt[1] = s_tail[3]; P1.zt[2] = s_tail[5];
@@ -234,18 +240,21 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
 
     for (int it = 0; it < n_iter; it++) {
         dec_pass(P1, tid, nw, K);
+        for (int p = tid; p < NP; p += nt) Lsa2[p] = (int16_t)((int)LsI[p] + (int)Le1[piT[p]]);   // interleave the extrinsic
+        __syncthreads();
         dec_pass(P2, tid, nw, K);
         for (int j = tid; j < K; j += nt) {
             int acc = 0;
             const int e = csr_start[j + 1];
             for (int t = csr_start[j]; t < e; t++) acc += (int)Le2[csr_pos[t]];
-            La1[(j & 31) * nw + (j >> 5)] = (int16_t)clampi(acc, -LA_LIM, LA_LIM);
+            const int p = (j & 31) * nw + (j >> 5);
+            Lsa1[p] = (int16_t)((int)Ls[p] + clampi(acc, -LA_LIM, LA_LIM));                      // de-interleave, combine
         }
         __syncthreads();
     }
     for (int j = tid; j < K; j += nt) {
         const int p = (j & 31) * nw + (j >> 5);
-        out[(size_t)cb * K + j] = ((int)Ls[p] + (int)La1[p] + (int)Le1[p] >= 0) ? 0 : 1;
+        out[(size_t)cb * K + j] = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
     }
 }
 
@@ -282,7 +291,7 @@ int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
             ctx->mlm[K] = mt;
         } else mt = it->second;
     }
-    const size_t smem = (size_t)16 * NP + (size_t)4 * nw * 8 * 4 + (size_t)3 * NP * 2 + (size_t)4 * NP;
+    const size_t smem = (size_t)16 * NP + (size_t)4 * nw * 8 * 4 + (size_t)4 * NP * 2 + (size_t)4 * NP;
     LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = ((nw + 31) / 32) * 32;
     turbo_mlm_kernel<<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits);

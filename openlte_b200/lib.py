@@ -51,6 +51,8 @@ SYMBOLS = {
     "lteb200_pdsch_decode_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_pdsch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _vp, _u32, _u32, C.c_uint8, _i, _i, _vp, _vp]),
     "lteb200_pdsch_demod_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "lteb200_ofdm_demod_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp]),
+    "lteb200_chan_est_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "lteb200_dl_receive_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_dl_receive_host": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
     "lteb200_find_coarse_timing_and_freq_offset": (_i, [_vp, _vp, _vp, _ll, _i, _u32, _vp, _vp, _vp]),

@@ -67,3 +67,65 @@ def rate_match_turbo(d, E, rv=0, C=1, tx_mode=1, N_soft=250368, M_dl_harq=8, cha
     d = np.ascontiguousarray(d, np.uint8); D = d.size // 3; out = np.zeros(E, np.uint8)
     lib().op_rate_match_turbo(_p(d), D, C, tx_mode, N_soft, M_dl_harq, chan_type, rv, E, _p(out))
     return out
+
+
+def prs_c(c_init, n):
+    out = np.zeros(n, np.uint8); lib().op_prs_c(C.c_uint32(c_init), n, _p(out)); return out
+
+
+def crc(bits, poly=0x1864CFB, n_p=24):
+    b = np.ascontiguousarray(bits, np.uint8); return int(lib().op_crc(_p(b), int(b.size), C.c_uint32(poly), n_p))
+
+
+def segmentation_params(tbs):
+    K = C.c_int(0); F = C.c_int(0); Cc = C.c_int(0)
+    lib().op_segmentation_params(tbs, C.byref(K), C.byref(F), C.byref(Cc)); return K.value, F.value, Cc.value
+
+
+def zf_1ant(y_re, y_im, h_re, h_im):
+    a = [np.ascontiguousarray(v, np.float32) for v in (y_re, y_im, h_re, h_im)]
+    xr = np.zeros_like(a[0]); xi = np.zeros_like(a[0])
+    lib().op_zf_1ant(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), int(a[0].size), _p(xr), _p(xi)); return xr, xi
+
+
+def demap(d_re, d_im, mod):
+    r = np.ascontiguousarray(d_re, np.float32); i = np.ascontiguousarray(d_im, np.float32)
+    out = np.zeros(6 * r.size, np.int8); n = lib().op_demap(_p(r), _p(i), int(r.size), mod, _p(out)); return out[:n]
+
+
+def pdsch_re_indices(N_rb_dl, N_id_cell, N_ant, subfr, cfi, prb, prb1=None):
+    p0 = np.ascontiguousarray(prb, np.int32); p1 = p0 if prb1 is None else np.ascontiguousarray(prb1, np.int32)
+    out = np.zeros(14 * 12 * p0.size, np.int32)
+    n = lib().op_pdsch_re_indices(N_rb_dl, N_id_cell, N_ant, subfr, cfi, int(p0.size), _p(p0), _p(p1), _p(out)); return out[:n]
+
+
+def fft_forward(re, im):
+    re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32)
+    o_re = np.zeros_like(re); o_im = np.zeros_like(im)
+    lib().op_fft_forward(int(re.size), _p(re), _p(im), _p(o_re), _p(o_im)); return o_re, o_im
+
+
+def crs(N_s, L, N_id_cell):
+    re = np.zeros(220, np.float32); im = np.zeros(220, np.float32); lib().op_crs(N_s, L, N_id_cell, _p(re), _p(im)); return re, im
+
+
+def chan_est(rx_re, rx_im, N_rb_dl, subfr, N_id_cell, N_ant):
+    rx_re = np.ascontiguousarray(rx_re, np.float32); rx_im = np.ascontiguousarray(rx_im, np.float32)
+    ce_re = np.zeros((4, 16, 1200), np.float32); ce_im = np.zeros((4, 16, 1200), np.float32)
+    lib().op_chan_est(_p(rx_re), _p(rx_im), N_rb_dl, subfr, N_id_cell, N_ant, _p(ce_re), _p(ce_im)); return ce_re, ce_im
+
+
+def get_dl_subframe_and_ce(i_samps, q_samps, fs_idx, N_rb_dl, frame_start_idx, subfr, N_id_cell, N_ant):
+    rx_re = np.zeros((16, 1200), np.float32); rx_im = np.zeros((16, 1200), np.float32)
+    ce_re = np.zeros((4, 16, 1200), np.float32); ce_im = np.zeros((4, 16, 1200), np.float32)
+    lib().op_get_dl_subframe_and_ce(_p(i_samps), _p(q_samps), fs_idx, N_rb_dl, C.c_uint32(frame_start_idx), subfr, N_id_cell, N_ant,
+                                    _p(rx_re), _p(rx_im), _p(ce_re), _p(ce_im))
+    return rx_re, rx_im, ce_re, ce_im
+
+
+def pdsch_decode(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, subfr, cfi, mod, prb, tbs, rnti, rv=0, turbo_mode=0, n_iter=8):
+    prb = np.ascontiguousarray(prb, np.int32); out = np.zeros(tbs + 32, np.uint8)
+    a = [np.ascontiguousarray(v, np.float32) for v in (rx_re, rx_im, ce_re, ce_im)]
+    rc = lib().op_pdsch_decode(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), N_rb_dl, N_id_cell, subfr, cfi, mod, int(prb.size), _p(prb), tbs, rv,
+                               rnti, turbo_mode, n_iter, _p(out))
+    return rc, out[:tbs]

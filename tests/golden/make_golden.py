@@ -1,0 +1,119 @@
+"""Generates the fixtures under tests/golden/ from the REFERENCE ITSELF (oracle/_ref = /root/reference's
+liblte_phy.cc compiled unmodified).  Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference; the -m gpu tests read only these committed fixtures (and oracle/_ref/*.so,
+which travels with the snapshot).  Every array is float32/int8/uint8 to keep the files small.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref  # noqa: E402
+from util import ref_loopback  # noqa: E402
+
+FS_IDX = {1.92: 0, 3.84: 1, 7.68: 2, 15.36: 3, 30.72: 4}
+QM = {0: 1, 1: 2, 2: 4, 3: 6}
+
+
+def loopback_case(name, fs, N_rb_dl, cell, subfr, mod, prb, tbs, rnti, N_ant_ce=1, gain=0.7 * np.exp(0.9j), noise=0.002, cfi=2, seed=0,
+                  frame_start=0):
+    lb = ref_loopback(ref, subfr, [dict(mod=mod, prb=prb, tbs=tbs, rnti=rnti)], N_id_cell=cell, cfi=cfi, N_rb_dl=N_rb_dl, fs=fs, seed=seed,
+                      gain=gain, noise=noise, frame_start=frame_start)
+    phy = lb["phy"]
+    sf = ref.Subframe()
+    phy.get_dl_subframe_and_ce(lb["i"], lb["q"], frame_start, subfr, cell, N_ant_ce, sf)
+    rx_re, rx_im = sf.rx_symb_re.copy(), sf.rx_symb_im.copy()
+    ce_re, ce_im = sf.rx_ce_re.copy(), sf.rx_ce_im.copy()
+    # PDSCH decode uses the single-port estimate (the transmitter has one port)
+    sf1 = ref.Subframe()
+    phy.get_dl_subframe_and_ce(lb["i"], lb["q"], frame_start, subfr, cell, 1, sf1)
+    err, bits = phy.pdsch_decode(sf1, cfi, cell, 1, mod, prb, tbs, rnti)
+    from oracle import port
+    n_re = port.pdsch_re_indices(N_rb_dl, cell, 1, subfr, cfi, prb).size
+    G = n_re * QM[mod]
+    descr = phy.pdsch_scratch(1, G, np.float32)
+    # trim the sample arrays to what the receiver touches
+    n_keep = frame_start + (subfr + 1) * lb["n_sf"] + 3 * (128 << FS_IDX[fs]) * 2
+    np.savez_compressed(os.path.join(HERE, name), i=lb["i"][:n_keep], q=lb["q"][:n_keep], fs_idx=FS_IDX[fs], N_rb_dl=N_rb_dl, N_id_cell=cell,
+                        subfr=subfr, n_sf=lb["n_sf"], frame_start=frame_start, mod=mod, prb=np.array(prb, np.int32), tbs=tbs, rnti=rnti, cfi=cfi,
+                        N_ant_ce=N_ant_ce, tb=lb["tb"][0], ref_rx_re=rx_re, ref_rx_im=rx_im, ref_ce_re=ce_re[:, :14], ref_ce_im=ce_im[:, :14],
+                        ref_descramb=descr, ref_crc_ok=int(err == 0), ref_tb=bits)
+    print(name, "G", G, "ref err", err, "tb ok", np.array_equal(bits, lb["tb"][0]))
+
+
+def turbo_cases():
+    """A few reference-decoded code words per K (inputs + the reference's decoded bits and intermediates)."""
+    phy = ref.RefPhy()
+    rng = np.random.default_rng(42)
+    out = {}
+    for K in (40, 1024, 3584, 6144):
+        for sigma in (0.0, 0.5, 0.8):
+            c = rng.integers(0, 2, K).astype(np.uint8)
+            d = phy.turbo_encode(c)
+            x = (1.0 - 2.0 * d.astype(np.float32)).reshape(3, K + 4).T.reshape(-1)
+            x = (x + sigma * rng.standard_normal(x.size)).astype(np.float32)
+            if sigma == 0.5:
+                x[1::21] = 10000.0
+            key = f"K{K}_s{int(sigma * 10)}"
+            out[key + "_c"] = c
+            out[key + "_enc"] = d
+            out[key + "_x"] = x.astype(np.float16).astype(np.float32)  # store exactly representable values, half the bytes
+            out[key + "_dec"] = phy.turbo_decode(out[key + "_x"])
+            out[key + "_act1"] = phy.turbo_intermediate(0, K)
+    np.savez_compressed(os.path.join(HERE, "turbo_ref.npz"), **out)
+    print("turbo_ref.npz", len(out))
+
+
+def ratematch_cases():
+    phy = ref.RefPhy()
+    rng = np.random.default_rng(43)
+    out = {}
+    for K in (40, 1024, 6144):
+        D = K + 4
+        for rv in range(4):
+            for E in (3 * D, 6 * D + 8, 2 * D + 3):
+                d = rng.integers(0, 2, 3 * D).astype(np.uint8)
+                e = phy.rate_match_turbo(d, E, rv=rv)
+                llr = (rng.standard_normal(E) * 4).astype(np.float16).astype(np.float32)
+                llr[::19] = 10000.0
+                key = f"K{K}_rv{rv}_E{E}"
+                out[key + "_d"] = d; out[key + "_e"] = e; out[key + "_llr"] = llr.astype(np.float16)
+                out[key + "_un"] = phy.rate_unmatch_turbo(llr, D, rv=rv)
+    np.savez_compressed(os.path.join(HERE, "ratematch_ref.npz"), **out)
+    print("ratematch_ref.npz", len(out))
+
+
+def sequence_cases():
+    out = {}
+    for ci in (0, 1, 0x3FFF0123, (0xFFFF << 14) | (5 << 9), 12345678):
+        out[f"prs_{ci}"] = ref.prs_c(ci, 2000).astype(np.uint8)
+    rng = np.random.default_rng(44)
+    for n in (24, 144, 6120):
+        b = rng.integers(0, 2, n).astype(np.uint8)
+        out[f"crc_in_{n}"] = b
+        out[f"crc24a_{n}"] = ref.crc(b, 0); out[f"crc24b_{n}"] = ref.crc(b, 1); out[f"crc16_{n}"] = ref.crc(b, 2)
+    for (ns, l, cell) in ((0, 0, 0), (19, 4, 503), (7, 1, 77)):
+        re, im = ref.crs(ns, l, cell)
+        out[f"crs_{ns}_{l}_{cell}"] = np.stack([re, im])
+    for mod in (0, 1, 2, 3):
+        re = (rng.standard_normal(600) * 0.8).astype(np.float32); im = (rng.standard_normal(600) * 0.8).astype(np.float32)
+        re[:5] = 0; im[3:8] = 0
+        out[f"demap_in_{mod}"] = np.stack([re, im]); out[f"demap_out_{mod}"] = ref.mod_demap(re, im, mod)
+    np.savez_compressed(os.path.join(HERE, "sequences_ref.npz"), **out)
+    print("sequences_ref.npz", len(out))
+
+
+if __name__ == "__main__":
+    loopback_case("loop_64qam_c0_sf1.npz", 30.72, 100, 0, 1, 3, list(range(12)), 2216, 0x1234)
+    loopback_case("loop_qpsk_c77_sf5.npz", 30.72, 100, 77, 5, 1, list(range(40, 76)), 3240, 0x0A0B, N_ant_ce=2, seed=1)
+    loopback_case("loop_16qam_c150_sf0.npz", 30.72, 100, 150, 0, 2, list(range(41, 59)), 3112, 0x7FFF, seed=2)
+    loopback_case("loop_qpsk_5mhz_c301_sf3.npz", 7.68, 25, 301, 3, 1, list(range(2, 20)), 1544, 0x0042, N_ant_ce=4, seed=3, frame_start=137)
+    turbo_cases()
+    ratematch_cases()
+    sequence_cases()

@@ -1,0 +1,124 @@
+"""The oracle is pinned here (CPU only): every function of the restatement in oracle/port/ is compared with the
+fixtures generated from the reference itself (tests/golden/make_golden.py) and, where oracle/_ref is present, with
+the reference directly on fresh random inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from util import noisy_codeword
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    z = np.load(os.path.join(GOLD, name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def test_qpp_table_is_the_spec_and_pi_overflows_like_the_reference(port):
+    # every row of the table is a permutation in exact arithmetic ...
+    from oracle.port import qpp_pi
+    bad = []
+    import re
+    rows = re.findall(r"\{\s*(\d+),\s*(\d+),\s*(\d+)\}", open(os.path.join(os.path.dirname(GOLD), "..", "openlte_b200", "csrc", "qpp_table.h")).read())
+    assert len(rows) == 188
+    for K, f1, f2 in [(int(a), int(b), int(c)) for a, b, c in rows]:
+        exact = [(f1 * i + f2 * i * i) % K for i in range(K)]
+        assert len(set(exact)) == K
+        got = qpp_pi(K)
+        if not np.array_equal(got, np.array(exact, np.uint32)):
+            bad.append((K, len(set(got.tolist()))))
+    # ... and exactly 20 sizes differ from it under uint32 wrap-around, K = 6144 keeping 3955 distinct indices
+    assert len(bad) == 20 and (6144, 3955) in bad and (3584, 3576) in bad and (5248, 2500) in bad
+
+
+def test_turbo_against_reference_fixtures(port):
+    g = gold("turbo_ref.npz")
+    for K in (40, 1024, 3584, 6144):
+        for s in (0, 5, 8):
+            key = f"K{K}_s{s}"
+            assert np.array_equal(port.turbo_encode(g[key + "_c"]), g[key + "_enc"])
+            dec, dbg = port.turbo_decode_ref(g[key + "_x"], True)
+            assert np.array_equal(dec, g[key + "_dec"]), key
+            assert np.array_equal(dbg[0], g[key + "_act1"]), key
+            if s == 0:
+                assert np.array_equal(dec, g[key + "_c"])
+                assert np.array_equal(port.turbo_decode_mlm(g[key + "_x"], 8), g[key + "_c"])
+
+
+def test_ratematch_against_reference_fixtures(port):
+    g = gold("ratematch_ref.npz")
+    keys = sorted({k.rsplit("_", 1)[0] for k in g})
+    assert len(keys) == 36
+    for key in keys:
+        K = int(key.split("_")[0][1:]); rv = int(key.split("_")[1][2:]); E = int(key.split("_")[2][1:])
+        assert np.array_equal(port.rate_match_turbo(g[key + "_d"], E, rv=rv), g[key + "_e"]), key
+        assert np.array_equal(port.rate_unmatch_turbo(g[key + "_llr"].astype(np.float32), K + 4, rv=rv), g[key + "_un"]), key
+
+
+def test_sequences_crc_demap_against_reference_fixtures(port):
+    g = gold("sequences_ref.npz")
+    for ci in (0, 1, 0x3FFF0123, (0xFFFF << 14) | (5 << 9), 12345678):
+        assert np.array_equal(port.prs_c(ci, 2000), g[f"prs_{ci}"])
+    for n in (24, 144, 6120):
+        b = g[f"crc_in_{n}"]
+        as_int = lambda bits: int("".join(map(str, bits)), 2)
+        assert port.crc(b, 0x1864CFB, 24) == as_int(g[f"crc24a_{n}"])
+        assert port.crc(b, 0x1800063, 24) == as_int(g[f"crc24b_{n}"])
+        assert port.crc(b, 0x11021, 16) == as_int(g[f"crc16_{n}"])
+    for (ns, l, cell) in ((0, 0, 0), (19, 4, 503), (7, 1, 77)):
+        re, im = port.crs(ns, l, cell)
+        assert np.array_equal(np.stack([re, im]), g[f"crs_{ns}_{l}_{cell}"])
+    for mod in (0, 1, 2, 3):
+        re, im = g[f"demap_in_{mod}"]
+        assert np.array_equal(port.demap(re, im, mod), g[f"demap_out_{mod}"])
+    assert port.segmentation_params(144) == (168, 0, 1)
+    assert port.segmentation_params(6120) == (6144, 0, 1)
+    assert port.segmentation_params(100)[:2] == (128, 4)
+
+
+@pytest.mark.parametrize("name", ["loop_64qam_c0_sf1.npz", "loop_qpsk_c77_sf5.npz", "loop_16qam_c150_sf0.npz", "loop_qpsk_5mhz_c301_sf3.npz"])
+def test_frontend_against_reference_fixtures(port, name):
+    c = gold(name)
+    nsc = 12 * int(c["N_rb_dl"]); n_ant = int(c["N_ant_ce"])
+    # channel estimate from the reference's own grid: bit-identical (same libm, same operation order)
+    ce_re, ce_im = port.chan_est(c["ref_rx_re"], c["ref_rx_im"], int(c["N_rb_dl"]), int(c["subfr"]), int(c["N_id_cell"]), n_ant)
+    assert np.array_equal(ce_re[:n_ant, :14, :nsc], c["ref_ce_re"][:n_ant, :, :nsc])
+    assert np.array_equal(ce_im[:n_ant, :14, :nsc], c["ref_ce_im"][:n_ant, :, :nsc])
+    # OFDM demod: the port's DFT is double precision, the reference's is single: tolerance 2e-6 of the grid maximum
+    rx_re, rx_im, _, _ = port.get_dl_subframe_and_ce(c["i"], c["q"], int(c["fs_idx"]), int(c["N_rb_dl"]), int(c["frame_start"]), int(c["subfr"]),
+                                                     int(c["N_id_cell"]), 1)
+    sc = np.abs(c["ref_rx_re"]).max()
+    assert np.abs(rx_re - c["ref_rx_re"]).max() <= 2e-6 * sc and np.abs(rx_im - c["ref_rx_im"]).max() <= 2e-6 * sc
+    # RE extraction + ZF + demap + descramble: exactly the reference's pdsch_descramb_bits
+    ce1_re, ce1_im = port.chan_est(c["ref_rx_re"], c["ref_rx_im"], int(c["N_rb_dl"]), int(c["subfr"]), int(c["N_id_cell"]), 1)
+    idx = port.pdsch_re_indices(int(c["N_rb_dl"]), int(c["N_id_cell"]), 1, int(c["subfr"]), int(c["cfi"]), c["prb"])
+    # grid rows are 1200 wide in the reference struct; indices are L*1200+sc
+    xr, xi = port.zf_1ant(c["ref_rx_re"].reshape(-1)[idx], c["ref_rx_im"].reshape(-1)[idx], ce1_re[0].reshape(-1)[idx], ce1_im[0].reshape(-1)[idx])
+    soft = port.demap(xr, xi, int(c["mod"])).astype(np.float32)
+    cseq = port.prs_c((int(c["rnti"]) << 14) | (int(c["subfr"]) << 9) | int(c["N_id_cell"]), soft.size)
+    assert np.array_equal(soft * (1 - 2 * cseq.astype(np.float32)), c["ref_descramb"])
+    rc, bits = port.pdsch_decode(c["ref_rx_re"], c["ref_rx_im"], ce1_re[0], ce1_im[0], int(c["N_rb_dl"]), int(c["N_id_cell"]), int(c["subfr"]),
+                                 int(c["cfi"]), int(c["mod"]), c["prb"], int(c["tbs"]), int(c["rnti"]))
+    assert (rc == 0) == bool(c["ref_crc_ok"])
+    if rc == 0:
+        assert np.array_equal(bits, c["ref_tb"]) and np.array_equal(bits, c["tb"])
+    rc, bits = port.pdsch_decode(c["ref_rx_re"], c["ref_rx_im"], ce1_re[0], ce1_im[0], int(c["N_rb_dl"]), int(c["N_id_cell"]), int(c["subfr"]),
+                                 int(c["cfi"]), int(c["mod"]), c["prb"], int(c["tbs"]), int(c["rnti"]), turbo_mode=1)
+    assert rc == 0 and np.array_equal(bits, c["tb"])      # max-log-MAP also decodes the punctured case the reference fails (H11)
+
+
+def test_port_against_live_reference(port, refo):
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    phy = refo.RefPhy()
+    rng = np.random.default_rng(11)
+    for K in (48, 512, 5248, 6144):
+        for sigma in (0.0, 0.4, 0.9):
+            c, x = noisy_codeword(port, K, sigma, rng, sentinel_every=13 if sigma == 0.4 else 0)
+            assert np.array_equal(port.turbo_decode_ref(x), phy.turbo_decode(x))
+        D = K + 4
+        for rv in (0, 3):
+            e = (rng.standard_normal(3 * D + 77) * 2).astype(np.float32)
+            assert np.array_equal(port.rate_unmatch_turbo(e, D, rv=rv), phy.rate_unmatch_turbo(e, D, rv=rv))

@@ -37,8 +37,9 @@ def test_mode_a_bit_exact(ctx, port, refo, K):
         phy = refo.RefPhy()
         for b in range(0, xs.shape[0], 4):
             assert np.array_equal(got[b], phy.turbo_decode(xs[b])), f"K={K} block {b} differs from the reference itself"
-    # noise-free blocks decode to the transmitted bits (self-consistency of the reference codec)
-    for b in range(3):
+    # noise-free, unpunctured blocks decode to the transmitted bits (self-consistency of the reference codec,
+    # BASELINE.md P3); block 0 carries sentinels, i.e. is punctured, where the reference itself fails
+    for b in (1, 2):
         assert np.array_equal(got[b], cs[b])
 
 

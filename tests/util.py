@@ -24,3 +24,33 @@ def stream_ptr():
     import ctypes
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Synthetic downlink signal through the REFERENCE's own transmit functions: CRS +
+# PDSCH allocations -> IFFT, followed by a CRS-only subframe (the estimator reads symbols 14-15).
+def ref_loopback(refo, subfr, allocs, N_id_cell=0, cfi=2, N_rb_dl=100, fs=30.72, seed=0, gain=1.0 + 0j, noise=0.0,
+                 frame_start=0, n_extra=1):
+    """allocs: list of dict(mod, prb, tbs, rnti).  Returns dict with i/q sample arrays (float32), tb bits, phy handle."""
+    rng = np.random.default_rng(seed)
+    phy = refo.RefPhy(fs=fs, N_id_cell=N_id_cell, N_ant=1, N_rb_dl=N_rb_dl)
+    n_sf = {30.72: 30720, 15.36: 15360, 7.68: 7680, 3.84: 3840, 1.92: 1920}[fs]
+    total = frame_start + (subfr + 1 + n_extra) * n_sf + 4096
+    i_s = np.zeros(total, np.float32); q_s = np.zeros(total, np.float32)
+    tbs_bits = []
+    for k in range(1 + n_extra):
+        sf = refo.Subframe(); sf.clear(); sf.set_num((subfr + k) % 10)
+        phy.map_crs(sf, N_id_cell, 1)
+        if k == 0:
+            for a in allocs:
+                tb = rng.integers(0, 2, a["tbs"]).astype(np.uint8)
+                tbs_bits.append(tb)
+                phy.pdsch_encode(sf, cfi, N_id_cell, 1, a["mod"], a["prb"], a["tbs"], a["rnti"], tb, rv=a.get("rv", 0))
+        i_sf, q_sf = phy.create_dl_subframe(sf, 0, n_sf)
+        o = frame_start + (subfr + k) * n_sf
+        i_s[o:o + n_sf] = i_sf; q_s[o:o + n_sf] = q_sf
+    z = (i_s + 1j * q_s) * gain
+    if noise > 0:
+        z = z + noise * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+    return dict(i=np.ascontiguousarray(z.real.astype(np.float32)), q=np.ascontiguousarray(z.imag.astype(np.float32)),
+                tb=tbs_bits, phy=phy, n_sf=n_sf, frame_start=frame_start)
