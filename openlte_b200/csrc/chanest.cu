@@ -26,6 +26,22 @@ __device__ __forceinline__ float wrap_phase(float p1, float p2)
     return p1;
 }
 
+// CRS symbol i of port p sits in grid symbol crs_sym(p, i) with frequency offset (v + N_id_cell mod 6) mod 6 (liblte_phy.cc:5973-6014)
+__device__ __forceinline__ int crs_sym(int p, int i)
+{
+    if (p < 2) return i == 0 ? 0 : (i == 1 ? 4 : (i == 2 ? 7 : (i == 3 ? 11 : 14)));
+    return i == 0 ? 1 : (i == 1 ? 8 : 15);
+}
+__device__ __forceinline__ int crs_off(int p, int i, int vsh)
+{
+    int v;
+    if (p == 0) v = (i & 1) ? 3 : 0;
+    else if (p == 1) v = (i & 1) ? 0 : 3;
+    else if (p == 2) v = (i & 1) ? 3 : 0;
+    else v = (i & 1) ? 6 : 3;
+    return (v + vsh) % 6;
+}
+
 struct CeParams {
     int N_rb, nsc, N_ant, N_id_cell;
 };
@@ -42,21 +58,13 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
     const int vsh = P.N_id_cell % 6;
     const int n_crs = 2 * P.N_rb;
     const int N_sym = p < 2 ? 5 : 3;
-    int sym[5], off[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        int v;
-        if (p < 2) { const int s5[5] = {0, 4, 7, 11, 14}; sym[i] = s5[i]; v = ((i & 1) ^ p) ? 3 : 0; }
-        else { const int s3[5] = {1, 8, 15, 0, 0}; sym[i] = s3[i]; v = (p == 2) ? ((i & 1) ? 3 : 0) : ((i & 1) ? 6 : 3); }
-        off[i] = (v + vsh) % 6;
-    }
     const float2 *g = grid + (size_t)sf * 16 * P.nsc;
 
     // 1. LS estimate at the CRS tones -> polar
     for (int idx = threadIdx.x; idx < N_sym * n_crs; idx += blockDim.x) {
         const int i = idx / n_crs, j = idx - i * n_crs;
-        const int k = 6 * j + off[i];
-        const int s = sym[i], slot = (2 * sn + s / 7) % 20, l = s % 7;
+        const int k = 6 * j + crs_off(p, i, vsh);
+        const int s = crs_sym(p, i), slot = (2 * sn + s / 7) % 20, l = s % 7;
         const float2 rs = crs_tab[(slot * 3 + (l == 0 ? 0 : (l == 1 ? 1 : 2))) * 220 + j + 110 - P.N_rb];
         const float2 y = g[s * P.nsc + k];
         const float tr = __fadd_rn(__fmul_rn(y.x, rs.x), __fmul_rn(y.y, rs.y));
@@ -69,9 +77,10 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
     if (threadIdx.x < N_sym) {
         const int i = threadIdx.x;
         float *A = Ag + i * 1200;
-        float prev = A[off[i]];
+        const int of = crs_off(p, i, vsh);
+        float prev = A[of];
         for (int j = 1; j < n_crs; j++) {
-            const int k = 6 * j + off[i];
+            const int k = 6 * j + of;
             prev = wrap_phase(A[k], prev);
             A[k] = prev;
         }
@@ -81,18 +90,19 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
     for (int idx = threadIdx.x; idx < N_sym * (n_crs - 1); idx += blockDim.x) {
         const int i = idx / (n_crs - 1), j = idx - i * (n_crs - 1) + 1;
         float *M = Mg + i * 1200, *A = Ag + i * 1200;
-        const int k = 6 * j + off[i];
+        const int of = crs_off(p, i, vsh);
+        const int k = 6 * j + of;
         const float fm = __fdiv_rn(__fsub_rn(M[k], M[k - 6]), 6.0f), fa = __fdiv_rn(__fsub_rn(A[k], A[k - 6]), 6.0f);
         float m = M[k], a = A[k];
 #pragma unroll
         for (int z = 1; z < 6; z++) { m = __fsub_rn(m, fm); a = __fsub_rn(a, fa); M[k - z] = m; A[k - z] = a; }
         if (j == 1) {
             m = M[k - 6]; a = A[k - 6];
-            for (int z = 1; z < off[i] + 1; z++) { m = __fsub_rn(m, fm); a = __fsub_rn(a, fa); M[k - 6 - z] = m; A[k - 6 - z] = a; }
+            for (int z = 1; z < of + 1; z++) { m = __fsub_rn(m, fm); a = __fsub_rn(a, fa); M[k - 6 - z] = m; A[k - 6 - z] = a; }
         }
         if (j == n_crs - 1) {
             m = M[k]; a = A[k];
-            for (int z = 1; z < (5 - off[i]) + 1; z++) { m = __fsub_rn(m, fm); a = __fsub_rn(a, fa); M[k + z] = m; A[k + z] = a; }
+            for (int z = 1; z < (5 - of) + 1; z++) { m = __fsub_rn(m, fm); a = __fsub_rn(a, fa); M[k + z] = m; A[k + z] = a; }
         }
     }
     __syncthreads();
