@@ -83,7 +83,8 @@ extern "C" int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_s
     if (!(N_ant == 1 || N_ant == 2 || N_ant == 4) || fs_idx < 0 || fs_idx > 4) return LTEB200_ERR_ARGS;
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     const int n_sf_samps = 1920 << fs_idx;
-    const long long start = (long long)frame_start_idx + (long long)subfr_num * n_sf_samps;
+    // uint32 arithmetic as in the reference (liblte_phy.cc:5927): a frame that starts just before the buffer wraps back in
+    const long long start = (long long)(uint32_t)(frame_start_idx + (uint32_t)subfr_num * (uint32_t)n_sf_samps);
     // only the window [start, start + subframe + 2 symbols + margin) travels to the device
     const long long lo = start > 0 ? start - 1 : 0;
     long long hi = start + n_sf_samps + 3LL * ((128 << fs_idx) + (10 << fs_idx));   // symbols 14-15 of the window

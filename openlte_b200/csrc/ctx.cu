@@ -34,6 +34,13 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->arena_bytes = 0;
     c->launches = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
+    // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
+    // otherwise every host-pointer call would re-acquire gigabytes from the driver.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     *out = c;
     return LTEB200_OK;
 }

@@ -32,7 +32,9 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 }
 
 // grid: [n_sf][16][nsc] float2.  blockIdx.x = subframe * 16 + symbol.
-template <typename T>
+// WINDOWS == false: blockIdx.x = subframe*16 + symbol, start_idx[subframe] is the subframe start.
+// WINDOWS == true : blockIdx.x = window, start_idx[window] is the first sample of the N-sample DFT window; output row = window.
+template <typename T, bool WINDOWS>
 __global__ void __launch_bounds__(512)
 ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
                   const float2 *__restrict__ tw /*[N] e^{-2 pi i k/N}*/, float2 *__restrict__ grid)
@@ -42,8 +44,9 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
     const int sf = blockIdx.x >> 4, sym = blockIdx.x & 15;
     const int slot = sym / 7, l = sym % 7;
     // window start: slot start + (N+CP_else)*l (+CP_0-CP_else for l>0) + CP_l - 1   (one sample early, :8607-8622)
-    long long idx = start_idx[sf] + (long long)slot * P.slot + (long long)(P.N + P.cpe) * l + (l > 0 ? P.cp0 - P.cpe : 0) +
-                    (l == 0 ? P.cp0 : P.cpe) - 1;
+    long long idx = WINDOWS ? start_idx[blockIdx.x]
+                            : start_idx[sf] + (long long)slot * P.slot + (long long)(P.N + P.cpe) * l + (l > 0 ? P.cp0 - P.cpe : 0) +
+                                  (l == 0 ? P.cp0 : P.cpe) - 1;
     for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
         const long long s = idx + i;
         bufA[i] = (s >= 0 && s < n_samps) ? load_iq<T>(iq, s) : make_float2(0.f, 0.f);
@@ -82,7 +85,7 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
         float2 *t_ = src; src = dst; dst = t_;
     }
     // bins -> subcarriers (:8625-8634): symb[h+i] = X[i+1], symb[h-1-i] = X[N-1-i]
-    float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
+    float2 *out = grid + (WINDOWS ? (size_t)blockIdx.x : ((size_t)sf * 16 + sym)) * P.nsc;
     for (int k = threadIdx.x; k < 2 * P.h; k += blockDim.x) {
         const int bin = (k >= P.h) ? (k - P.h + 1) : (P.N - P.h + k);
         out[k] = src[bin];
@@ -140,10 +143,27 @@ int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long 
     const int threads = P.N / 4 < 64 ? 64 : (P.N / 4 > 512 ? 512 : P.N / 4);
     const size_t smem = sizeof(float2) * 2 * P.N;
     if (iq_fmt == LTEB200_IQ_F32)
-        ofdm_demod_kernel<float2><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        ofdm_demod_kernel<float2, false><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
     else if (iq_fmt == LTEB200_IQ_I8)
-        ofdm_demod_kernel<char2><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        ofdm_demod_kernel<char2, false><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
     else { lteb200_set_error(ctx, "unknown I/Q format %d", iq_fmt); return LTEB200_ERR_ARGS; }
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}
+
+// N-point forward DFT of arbitrary sample windows (float2 stream): row w of d_out = the 12*N_rb_dl used bins of window w.
+int fft_windows_launch(lteb200_ctx *ctx, const float *d_iq, long long n_samps, int fs_idx, int N_rb_dl, const long long *d_win_start, int n_win,
+                       float *d_out, cudaStream_t stream)
+{
+    OfdmParams P;
+    P.N = 128 << fs_idx; P.log2N = 7 + fs_idx; P.cp0 = 10 << fs_idx; P.cpe = 9 << fs_idx; P.slot = 960 << fs_idx;
+    P.h = 6 * N_rb_dl; P.nsc = 12 * N_rb_dl;
+    float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, P.N, &tw);
+    if (rc) return rc;
+    const int threads = P.N / 4 < 64 ? 64 : (P.N / 4 > 512 ? 512 : P.N / 4);
+    ofdm_demod_kernel<float2, true><<<n_win, threads, sizeof(float2) * 2 * P.N, stream>>>((const float2 *)d_iq, n_samps, d_win_start, P, tw, (float2 *)d_out);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;

@@ -129,3 +129,23 @@ def pdsch_decode(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, subfr, cfi, mod
     rc = lib().op_pdsch_decode(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), N_rb_dl, N_id_cell, subfr, cfi, mod, int(prb.size), _p(prb), tbs, rv,
                                rnti, turbo_mode, n_iter, _p(out))
     return rc, out[:tbs]
+
+
+def find_coarse_timing(i_s, q_s, fs_idx, N_slots):
+    fo = np.zeros(5, np.float32); ss = np.zeros((5, 7), np.uint32); n = C.c_int(0)
+    lib().op_find_coarse_timing(_p(i_s), _p(q_s), fs_idx, N_slots, _p(fo), _p(ss), C.byref(n))
+    return fo, ss, n.value
+
+
+def find_pss(i_s, q_s, fs_idx, N_rb_dl, symb_starts):
+    ss = np.ascontiguousarray(symb_starts, np.uint32).copy()
+    a = C.c_uint32(0); b = C.c_uint32(0); th = C.c_float(0); fo = C.c_float(0)
+    lib().op_find_pss(_p(i_s), _p(q_s), fs_idx, N_rb_dl, _p(ss), C.byref(a), C.byref(b), C.byref(th), C.byref(fo))
+    return ss, a.value, b.value, th.value, fo.value
+
+
+def find_sss(i_s, q_s, fs_idx, N_rb_dl, N_id_2, symb_starts, pss_thresh):
+    ss = np.ascontiguousarray(symb_starts, np.uint32).copy()
+    a = C.c_uint32(0); b = C.c_uint32(0)
+    rc = lib().op_find_sss(_p(i_s), _p(q_s), fs_idx, N_rb_dl, C.c_uint32(N_id_2), _p(ss), C.c_float(pss_thresh), C.byref(a), C.byref(b))
+    return rc, ss, a.value, b.value

@@ -109,7 +109,37 @@ def sequence_cases():
     print("sequences_ref.npz", len(out))
 
 
+def capture_case():
+    """BASELINE config 1: the first 340,000 samples of the reference's shipped capture (20 MHz, cell 0) and what the
+    reference finds in them: coarse timing (20 slots), PSS, SSS, and SIB1 of the frame that starts 15 samples before the
+    buffer (sfn even) -- PDCCH decode supplies the allocation, PDSCH decode the 144 transport-block bits."""
+    raw = np.fromfile("/root/reference/Test captures/LTE_test_file_int8.bin", dtype=np.int8)
+    N = 340000
+    iq = raw[:2 * N].reshape(N, 2).copy()
+    i = np.ascontiguousarray(iq[:, 0].astype(np.float32)); q = np.ascontiguousarray(iq[:, 1].astype(np.float32))
+    phy = ref.RefPhy(fs=30.72, N_id_cell=0xFFFF, N_ant=4, N_rb_dl=6)
+    err, fo, ss, n = phy.find_coarse_timing(i, q, 20)
+    abs_corr = phy.timing_abs_corr(15360)
+    err, ss2, nid2, ps, th, f = phy.find_pss(i, q, ss[0])
+    err, ss3, nid1, fsi = phy.find_sss(i, q, nid2, ss2, th)
+    phy.update_n_rb_dl(100)
+    sf = ref.Subframe()
+    fs0 = (fsi - 307200) & 0xFFFFFFFF
+    phy.get_dl_subframe_and_ce(i, q, fs0, 5, 3 * nid1 + nid2, 1, sf)
+    err, cfi, allocs = phy.pdcch_decode(sf, 0, 1)
+    a = allocs[0]
+    err, bits = phy.pdsch_decode(sf, cfi, 0, 1, a["mod_type"], a["prb"], a["tbs"], a["rnti"], rv=a["rv_idx"], tx_mode=a["tx_mode"])
+    assert err == 0
+    np.savez_compressed(os.path.join(HERE, "capture_cfg1.npz"), iq=iq, coarse_n=n, coarse_fo=fo, coarse_ss=ss, pss_ss=ss2, N_id_2=nid2, pss_symb=ps,
+                        pss_thresh=np.float32(th), pss_fo=np.float32(f), sss_ss=ss3, N_id_1=nid1, frame_start_idx=fsi, sib1_frame_start=np.uint32(fs0),
+                        cfi=cfi, rnti=a["rnti"], tbs=a["tbs"], mod=a["mod_type"], rv=a["rv_idx"], prb=np.array(a["prb"], np.int32), sib1_bits=bits,
+                        sib1_rx_re=sf.rx_symb_re.copy(), sib1_rx_im=sf.rx_symb_im.copy(), sib1_ce_re=sf.rx_ce_re[0, :14].copy(),
+                        sib1_ce_im=sf.rx_ce_im[0, :14].copy())
+    print("capture_cfg1.npz", n, ss[0][0], nid2, ps, th, nid1, fsi, "".join(map(str, bits)))
+
+
 if __name__ == "__main__":
+    capture_case()
     loopback_case("loop_64qam_c0_sf1.npz", 30.72, 100, 0, 1, 3, list(range(12)), 2216, 0x1234)
     loopback_case("loop_qpsk_c77_sf5.npz", 30.72, 100, 77, 5, 1, list(range(40, 76)), 3240, 0x0A0B, N_ant_ce=2, seed=1)
     loopback_case("loop_16qam_c150_sf0.npz", 30.72, 100, 150, 0, 2, list(range(41, 59)), 3112, 0x7FFF, seed=2)
