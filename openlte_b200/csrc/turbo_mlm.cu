@@ -8,181 +8,184 @@
 // restated on the CPU in oracle/port/turbo_mlm.cc (the bit-exact twin the tests compare against).
 //
 // B200 mapping: one CTA per code block, everything of the block resident in shared memory for all iterations
-// (LLRs int8, extrinsics int16, forward metrics of every window int16: 192 KB at K = 6144, so one CTA of
-// 192 threads per SM); one thread per 32-step window holds the 8 forward/backward state metrics in
+// (LLRs int8, extrinsics int16, forward metrics of every step int16, interleaver tables: 222 KB at K = 6144, so one CTA of
+// 384 threads per SM); one thread per 16-step window holds the 8 forward/backward state metrics in
 // registers (int32, DPX add-max), windows are coupled by state-metric propagation from the previous
 // iteration, so all K/32 windows of a block advance in parallel without warm-up recursions.  Shared-memory
 // arrays use a window-transposed layout pos(k) = (k mod 32)*nw + k/32 so that at every step the threads of a
 // warp touch consecutive addresses (conflict free).  No tensor cores (no contraction on this path).
 #include "common.cuh"
 
+#ifndef MLM_WIN
+#define MLM_WIN 16   // window length (steps per thread); oracle/port/turbo_mlm.cc must use the same value
+#endif
+
 namespace {
 
-constexpr int WIN = 32;
-constexpr int NEG = -(1 << 28);
-constexpr int LE_LIM = 1023, LA_LIM = 2047;
+constexpr int NEG = -8000;
+constexpr int LE_LIM = 1023, LA_LIM = 1023;
 
 __host__ __device__ constexpr int tr_a(int S, int u) { return u ^ ((S >> 1) & 1) ^ (S & 1); }
 __host__ __device__ constexpr int tr_par(int S, int u) { return tr_a(S, u) ^ ((S >> 2) & 1) ^ (S & 1); }
 __host__ __device__ constexpr int tr_nxt(int S, int u) { return (tr_a(S, u) << 2) | (S >> 1); }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+__device__ __forceinline__ int qf(float v, float maxv) { return __float2int_rz(__fdiv_rn(__fmul_rn(v, 127.0f), maxv)); }  // NaN -> 0
 
-struct Gam {
-    int g[2][2];  // [u][p]
-    __device__ __forceinline__ Gam(int ls, int lp)
-    {
-        g[0][0] = ls + lp; g[0][1] = ls; g[1][0] = lp; g[1][1] = 0;
-    }
-};
+// two int16 lanes per register: lo = bits 0..15, hi = bits 16..31
+__device__ __forceinline__ uint32_t pk(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+__device__ __forceinline__ uint32_t lolo(uint32_t x, uint32_t y) { return __byte_perm(x, y, 0x5410); }
+__device__ __forceinline__ uint32_t hihi(uint32_t x, uint32_t y) { return __byte_perm(x, y, 0x7632); }
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t x) { return (int)x >> 16; }
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }                       // VIADD.16x2
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }                      // VIMNMX.S16x2
+__device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }  // VIADDMNMX.S16x2
 
-__device__ __forceinline__ int qf(float v, float maxv)
-{
-    return __float2int_rz(__fdiv_rn(__fmul_rn(v, 127.0f), maxv));  // NaN -> 0
-}
-
+// State metrics of the 8-state trellis, two states per register.
+//   forward  (alpha): e01 = (a0,a2)  e23 = (a4,a6)  o01 = (a1,a3)  o23 = (a5,a7)
+//   backward (beta) : ba  = (b0,b5)  bb  = (b2,b7)  bc  = (b4,b1)  bd  = (b6,b3)
+// Predecessors of state d are 2(d&3) and 2(d&3)+1, so the even/odd split makes every add-compare-select a vertical
+// 16x2 operation; one byte-permute per register restores the layout for the next step.
 struct Pass {
-    // per-block shared arrays (window-transposed)
-    const int16_t *Lsa;   // systematic + a-priori LLR, prepared before the pass
+    const int16_t *Lsa;   // systematic + a-priori LLR (window-transposed), prepared before the pass
     const int8_t *Lp;
     int16_t *LeOut;
-    int4 *st;             // [32][nw] packed 8 x int16
-    int *bA, *bB;         // [nw][8]
+    uint4 *st;            // [WIN][nw] forward metrics of every step (raw, 8 x int16)
+    uint4 *bA, *bB;       // [nw] window-boundary metrics carried to the next iteration
     int xt[3], zt[3];
 };
 
-__device__ __forceinline__ int pack_sat(int lo, int hi)
+// NT: compile-time row stride of every window-transposed array (the largest window count, K = 6144), so that after full
+// unrolling every shared-memory access of step i is `base + constant`.
+template <int WIN, int NT, bool FWD_NORM>
+__device__ __forceinline__ void fwd_step(uint32_t &e01, uint32_t &e23, uint32_t &o01, uint32_t &o23, int ls, int lp)
 {
-    int r;
-    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));  // {sat16(hi), sat16(lo)}
-    return r;
+    // the state vector is re-referenced to alpha(0) on every 4th step only: four steps add at most 4*1277 to a spread of 3831
+    const int dl = FWD_NORM ? lo16(e01) : 0;
+    const int g11 = -dl, g01 = ls - dl, g10 = lp - dl, g00 = g01 + lp;
+    const uint32_t Ga = pk(g00, g10), Gb = pk(g11, g01), Gc = pk(g01, g11), Gd = pk(g10, g00);
+    const uint32_t n01 = addmax2(e01, Ga, add2(o01, Gb));
+    const uint32_t n23 = addmax2(e23, Gc, add2(o23, Gd));
+    const uint32_t n45 = addmax2(e01, Gb, add2(o01, Ga));
+    const uint32_t n67 = addmax2(e23, Gd, add2(o23, Gc));
+    e01 = lolo(n01, n23); o01 = hihi(n01, n23); e23 = lolo(n45, n67); o23 = hihi(n45, n67);
 }
 
+template <bool BWD_NORM>
+__device__ __forceinline__ int bwd_step(uint32_t &ba, uint32_t &bb, uint32_t &bc, uint32_t &bd, const uint4 al, int ls, int lp)
+{
+    const int dl = BWD_NORM ? lo16(ba) : 0;                 // beta'(0)
+    const int g11 = -dl, g01 = ls - dl, g10 = lp - dl, g00 = g01 + lp;
+    const uint32_t G0a = pk(g00, g01), G0b = pk(g01, g00), G1a = pk(g11, g10), G1b = pk(g10, g11);
+    // gamma + beta' of the 16 transitions, grouped by the layout of their source state
+    const uint32_t x0e01 = add2(G0a, ba), x0e23 = add2(G0b, bb), x0o01 = add2(G0a, bc), x0o23 = add2(G0b, bd);
+    const uint32_t x1e01 = add2(G1a, bc), x1e23 = add2(G1b, bd), x1o01 = add2(G1a, ba), x1o23 = add2(G1b, bb);
+    const uint32_t t0 = addmax2(al.w, x0o23, addmax2(al.z, x0o01, addmax2(al.y, x0e23, add2(al.x, x0e01))));
+    const uint32_t t1 = addmax2(al.w, x1o23, addmax2(al.z, x1o01, addmax2(al.y, x1e23, add2(al.x, x1e01))));
+    const uint32_t mm = max2(lolo(t0, t1), hihi(t0, t1));   // (max over u=0 transitions, max over u=1 transitions)
+    const uint32_t ne01 = max2(x0e01, x1e01), ne23 = max2(x0e23, x1e23), no01 = max2(x0o01, x1o01), no23 = max2(x0o23, x1o23);
+    ba = lolo(ne01, no23); bb = hihi(ne01, no23); bc = lolo(ne23, no01); bd = hihi(ne23, no01);
+    const int L = lo16(mm) - hi16(mm);
+    return clampi(((L - ls) * 3) >> 2, -LE_LIM, LE_LIM);
+}
+
+template <int WIN, int NT>
 __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
 {
     const bool active = w < nw;
     const int n = active ? min(WIN, K - WIN * w) : 0;
-    int a[8], b[8];
+    uint32_t e01 = 0, e23 = 0, o01 = 0, o23 = 0, ba = 0, bb = 0, bc = 0, bd = 0;
     if (active) {
-        if (w == 0) {
-            a[0] = 0;
-#pragma unroll
-            for (int s = 1; s < 8; s++) a[s] = NEG;
-        } else {
-#pragma unroll
-            for (int s = 0; s < 8; s++) a[s] = P.bA[w * 8 + s];
-        }
+        if (w == 0) { e01 = pk(0, NEG); e23 = pk(NEG, NEG); o01 = e23; o23 = e23; }
+        else { const uint4 v = P.bA[w]; e01 = v.x; e23 = v.y; o01 = v.z; o23 = v.w; }
         if (w == nw - 1) {
-            // beta at time K: three forced termination steps ending in state 0
+            // beta at time K: three forced termination steps (u = feedback, so the register input is 0) ending in state 0
+            int b[8];
             b[0] = 0;
 #pragma unroll
             for (int s = 1; s < 8; s++) b[s] = NEG;
 #pragma unroll
             for (int t = 2; t >= 0; t--) {
                 int nb[8];
-                const Gam G(P.xt[t], P.zt[t]);
+                const int ls = P.xt[t], lp = P.zt[t], b0 = b[0];
 #pragma unroll
                 for (int S = 0; S < 8; S++) {
                     const int u = ((S >> 1) & 1) ^ (S & 1);
-                    nb[S] = max(G.g[u][tr_par(S, u)] + b[tr_nxt(S, u)], NEG);
+                    const int g = (u == 0 ? ls : 0) + (tr_par(S, u) == 0 ? lp : 0);
+                    nb[S] = max(g - b0 + b[tr_nxt(S, u)], NEG);
                 }
 #pragma unroll
                 for (int S = 0; S < 8; S++) b[S] = nb[S];
             }
-        } else {
-#pragma unroll
-            for (int s = 0; s < 8; s++) b[s] = P.bB[w * 8 + s];
-        }
+            ba = pk(b[0], b[5]); bb = pk(b[2], b[7]); bc = pk(b[4], b[1]); bd = pk(b[6], b[3]);
+        } else { const uint4 v = P.bB[w]; ba = v.x; bb = v.y; bc = v.z; bd = v.w; }
     }
-    __syncthreads();  // all boundaries of the previous iteration are read before any is overwritten
+    __syncthreads();  // every boundary of the previous iteration is read before any is overwritten
 
-    // ---- forward (inputs of step i+1 are fetched while step i computes)
-    int ls_n = 0, lp_n = 0;
-    if (n > 0) { ls_n = P.Lsa[w]; lp_n = P.Lp[w]; }
-    for (int i = 0; i < n; i++) {
-        const int p = i * nw + w;
-        const int ls = ls_n, lp = lp_n;
-        if (i + 1 < n) { ls_n = P.Lsa[p + nw]; lp_n = P.Lp[p + nw]; }
-        {
-            const int a0 = a[0];
-            int4 pk;
-            pk.x = pack_sat(0, a[1] - a0); pk.y = pack_sat(a[2] - a0, a[3] - a0);
-            pk.z = pack_sat(a[4] - a0, a[5] - a0); pk.w = pack_sat(a[6] - a0, a[7] - a0);
-            P.st[p] = pk;
+    const int16_t *Lsa = P.Lsa + w;
+    const int8_t *Lp = P.Lp + w;
+    uint4 *st = P.st + w;
+    int16_t *Le = P.LeOut + w;
+    if (n == WIN) {
+        // ---- full window: straight-line code, all addresses are base + constant.  The window's inputs are fetched
+        // up front (they do not depend on the recursion) so that no shared-memory latency sits on the dependent chain.
+        uint32_t in[WIN];
+#pragma unroll
+        for (int i = 0; i < WIN; i++) in[i] = pk((int)Lsa[i * NT], (int)Lp[i * NT]);   // (Lsa, Lp)
+#pragma unroll
+        for (int i = 0; i < WIN; i++) {
+            st[i * NT] = make_uint4(e01, e23, o01, o23);
+            if ((i & 3) == 0) fwd_step<WIN, NT, true>(e01, e23, o01, o23, lo16(in[i]), hi16(in[i]));
+            else fwd_step<WIN, NT, false>(e01, e23, o01, o23, lo16(in[i]), hi16(in[i]));
         }
-        const Gam G(ls, lp);
-        int na[8];
+        if (w + 1 < nw) P.bA[w + 1] = make_uint4(e01, e23, o01, o23);
+        uint4 a0 = st[(WIN - 1) * NT], a1 = st[(WIN - 2) * NT];                          // forward metrics, two steps ahead
 #pragma unroll
-        for (int d = 0; d < 8; d++) {
-            // predecessors of d: S = 2*(d&3) + s3 ; the input that leads S -> d is u = (d>>2) ^ s2 ^ s3
-            const int S0 = 2 * (d & 3), S1 = S0 + 1;
-            const int u0 = (d >> 2) ^ ((S0 >> 1) & 1) ^ (S0 & 1), u1 = (d >> 2) ^ ((S1 >> 1) & 1) ^ (S1 & 1);
-            na[d] = __viaddmax_s32(a[S0], G.g[u0][tr_par(S0, u0)], a[S1] + G.g[u1][tr_par(S1, u1)]);
+        for (int i = WIN - 1; i >= 0; i--) {
+            const uint4 al = a0;
+            a0 = a1;
+            if (i >= 2) a1 = st[(i - 2) * NT];
+            if ((i & 3) == 3) Le[i * NT] = (int16_t)bwd_step<true>(ba, bb, bc, bd, al, lo16(in[i]), hi16(in[i]));
+            else Le[i * NT] = (int16_t)bwd_step<false>(ba, bb, bc, bd, al, lo16(in[i]), hi16(in[i]));
         }
-#pragma unroll
-        for (int s = 0; s < 8; s++) a[s] = na[s];
-    }
-    if (active && w + 1 < nw) {
-        int mx = a[0];
-#pragma unroll
-        for (int s = 1; s < 8; s++) mx = max(mx, a[s]);
-#pragma unroll
-        for (int s = 0; s < 8; s++) P.bA[(w + 1) * 8 + s] = max(a[s] - mx, NEG);
-    }
-    // ---- backward + LLR
-    int4 pk_n = make_int4(0, 0, 0, 0);
-    if (n > 0) { const int p = (n - 1) * nw + w; ls_n = P.Lsa[p]; lp_n = P.Lp[p]; pk_n = P.st[p]; }
-    for (int i = n - 1; i >= 0; i--) {
-        const int p = i * nw + w;
-        const int ls = ls_n, lp = lp_n;
-        const int4 pk = pk_n;
-        if (i > 0) { ls_n = P.Lsa[p - nw]; lp_n = P.Lp[p - nw]; pk_n = P.st[p - nw]; }
-        const Gam G(ls, lp);
-        int al[8];
-        al[0] = (int)(short)(pk.x & 0xffff); al[1] = pk.x >> 16;
-        al[2] = (int)(short)(pk.y & 0xffff); al[3] = pk.y >> 16;
-        al[4] = (int)(short)(pk.z & 0xffff); al[5] = pk.z >> 16;
-        al[6] = (int)(short)(pk.w & 0xffff); al[7] = pk.w >> 16;
-        int nb[8], m0 = 0, m1 = 0;
-#pragma unroll
-        for (int S = 0; S < 8; S++) {
-            const int g0 = G.g[0][tr_par(S, 0)] + b[tr_nxt(S, 0)];
-            const int g1 = G.g[1][tr_par(S, 1)] + b[tr_nxt(S, 1)];
-            nb[S] = max(g0, g1);
-            if (S == 0) { m0 = al[0] + g0; m1 = al[0] + g1; }
-            else { m0 = __viaddmax_s32(al[S], g0, m0); m1 = __viaddmax_s32(al[S], g1, m1); }
+        if (w > 0) P.bB[w - 1] = make_uint4(ba, bb, bc, bd);
+    } else if (n > 0) {
+        // ---- the short last window of block sizes that are not a multiple of WIN
+        for (int i = 0; i < n; i++) {
+            st[i * NT] = make_uint4(e01, e23, o01, o23);
+            if ((i & 3) == 0) fwd_step<WIN, NT, true>(e01, e23, o01, o23, Lsa[i * NT], Lp[i * NT]);
+            else fwd_step<WIN, NT, false>(e01, e23, o01, o23, Lsa[i * NT], Lp[i * NT]);
         }
-#pragma unroll
-        for (int S = 0; S < 8; S++) b[S] = nb[S];
-        const int L = m0 - m1;
-        P.LeOut[p] = (int16_t)clampi(((L - ls) * 3) >> 2, -LE_LIM, LE_LIM);
-    }
-    if (active && w > 0) {
-        int mx = b[0];
-#pragma unroll
-        for (int s = 1; s < 8; s++) mx = max(mx, b[s]);
-#pragma unroll
-        for (int s = 0; s < 8; s++) P.bB[(w - 1) * 8 + s] = max(b[s] - mx, NEG);
+        for (int i = n - 1; i >= 0; i--) {
+            if ((i & 3) == 3) Le[i * NT] = (int16_t)bwd_step<true>(ba, bb, bc, bd, st[i * NT], Lsa[i * NT], Lp[i * NT]);
+            else Le[i * NT] = (int16_t)bwd_step<false>(ba, bb, bc, bd, st[i * NT], Lsa[i * NT], Lp[i * NT]);
+        }
+        if (w > 0) P.bB[w - 1] = make_uint4(ba, bb, bc, bd);
     }
     __syncthreads();
 }
 
-// piT  [32*nw] : pos(pi(k)) stored at pos(k)           (global, per K)
-// csr_start [K+1], csr_pos [K] : for natural index j, positions pos(i) of all i with pi(i) == j   (global, per K)
-__global__ void __launch_bounds__(192)
+// piT  [WIN*NT] : pos(pi(k)) stored at pos(k), pos(k) = (k mod WIN)*NT + k/WIN, NT = 6144/WIN    (global, per K)
+// csr_start [NP+1], csr_pos [K] : for POSITION p = pos(j), the positions pos(i) of all i with pi(i) == j   (global, per K)
+template <int WIN>
+__global__ void __launch_bounds__(WIN == 32 ? 192 : 384)
 turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_t *__restrict__ piT,
                  const uint16_t *__restrict__ csr_start, const uint16_t *__restrict__ csr_pos, uint8_t *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = 6144 / WIN;   // row stride of the window-transposed arrays (compile-time: largest block size)
     const int nw = (K + WIN - 1) / WIN;
-    const int NP = WIN * nw;  // padded length
-    int4 *st = (int4 *)smem_raw;                                   // 16*NP bytes
-    int *bA1 = (int *)(smem_raw + (size_t)16 * NP);                // 4 x nw*8 ints
-    int *bB1 = bA1 + nw * 8, *bA2 = bB1 + nw * 8, *bB2 = bA2 + nw * 8;
-    int16_t *Lsa1 = (int16_t *)(bB2 + nw * 8);   // Ls + a-priori of decoder 1 (natural order)
+    constexpr int NP = WIN * NT;     // padded length
+    uint4 *st = (uint4 *)smem_raw;                                  // 16*NP bytes
+    uint4 *bA1 = (uint4 *)(smem_raw + (size_t)16 * NP);             // 4 x nw uint4
+    uint4 *bB1 = bA1 + NT, *bA2 = bB1 + NT, *bB2 = bA2 + NT;
+    int16_t *Lsa1 = (int16_t *)(bB2 + NT);                          // Ls + a-priori of decoder 1 (natural order)
     int16_t *Lsa2 = Lsa1 + NP, *Le1 = Lsa2 + NP, *Le2 = Le1 + NP;
-    int8_t *Ls = (int8_t *)(Le2 + NP);
-    int8_t *LsI = Ls + NP, *Lp1 = LsI + NP, *Lp2 = Lp1 + NP;
+    uint16_t *s_piT = (uint16_t *)(Le2 + NP);                       // interleaver and its CSR inverse, staged once per block
+    uint16_t *s_cs = s_piT + NP, *s_cp = s_cs + (NP + 2);
+    int8_t *Ls = (int8_t *)(s_cp + NP);
+    int8_t *Lp1 = Ls + NP, *Lp2 = Lp1 + NP;
     __shared__ float s_red[32];
     __shared__ int s_tail[12];
 
@@ -206,8 +209,8 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     __syncthreads();
     const float maxv = s_red[0];
     // ---- quantise into the transposed arrays; zero the padding
-    for (int k = tid; k < NP; k += nt) {
-        const int p = (k & 31) * nw + (k >> 5);
+    for (int p = tid; p < NP; p += nt) {
+        const int k = (p % NT) * WIN + (p / NT);
         int q0 = 0, q1 = 0, q2 = 0;
         if (k < K) {
             float v0 = d[3 * k], v1 = d[3 * k + 1], v2 = d[3 * k + 2];
@@ -224,9 +227,10 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         if (v == LTEB200_RX_NULL_BIT) v = 0.f;
         s_tail[tid] = qf(v, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
     }
-    for (int i = tid; i < nw * 8 * 4; i += nt) bA1[i] = 0;  // bA1,bB1,bA2,bB2 are contiguous
-    __syncthreads();
-    for (int p = tid; p < NP; p += nt) LsI[p] = (p < NP) ? Ls[piT[p]] : 0;
+    for (int i = tid; i < NT * 4; i += nt) bA1[i] = make_uint4(0, 0, 0, 0);  // bA1,bB1,bA2,bB2 are contiguous
+    for (int p = tid; p < NP; p += nt) s_piT[p] = piT[p];
+    for (int j = tid; j <= NP; j += nt) s_cs[j] = csr_start[j];
+    for (int j = tid; j < K; j += nt) s_cp[j] = csr_pos[j];
     __syncthreads();
 
     Pass P1, P2;
@@ -239,21 +243,21 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     P2.zt[0] = s_tail[7]; P2.zt[1] = s_tail[9]; P2.zt[2] = s_tail[11];
 
     for (int it = 0; it < n_iter; it++) {
-        dec_pass(P1, tid, nw, K);
-        for (int p = tid; p < NP; p += nt) Lsa2[p] = (int16_t)((int)LsI[p] + (int)Le1[piT[p]]);   // interleave the extrinsic
+        dec_pass<WIN, NT>(P1, tid, nw, K);
+        for (int p = tid; p < NP; p += nt) { const int q = s_piT[p]; Lsa2[p] = (int16_t)((int)Ls[q] + (int)Le1[q]); }   // interleave
         __syncthreads();
-        dec_pass(P2, tid, nw, K);
-        for (int j = tid; j < K; j += nt) {
+        dec_pass<WIN, NT>(P2, tid, nw, K);
+        for (int p = tid; p < NP; p += nt) {                                                        // de-interleave, combine
             int acc = 0;
-            const int e = csr_start[j + 1];
-            for (int t = csr_start[j]; t < e; t++) acc += (int)Le2[csr_pos[t]];
-            const int p = (j & 31) * nw + (j >> 5);
-            Lsa1[p] = (int16_t)((int)Ls[p] + clampi(acc, -LA_LIM, LA_LIM));                      // de-interleave, combine
+            const int e = s_cs[p + 1];
+#pragma unroll 1
+            for (int t = s_cs[p]; t < e; t++) acc += (int)Le2[s_cp[t]];   // 0..3 entries (1 for every spec-correct block size)
+            Lsa1[p] = (int16_t)((int)Ls[p] + clampi(acc, -LA_LIM, LA_LIM));
         }
         __syncthreads();
     }
     for (int j = tid; j < K; j += nt) {
-        const int p = (j & 31) * nw + (j >> 5);
+        const int p = (j % WIN) * NT + (j / WIN);
         out[(size_t)cb * K + j] = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
     }
 }
@@ -267,34 +271,36 @@ int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
     QppTables qt;
     int rc = lteb200_get_qpp(ctx, K, &qt);  // validates K
     if (rc) return rc;
-    const int nw = (K + WIN - 1) / WIN, NP = WIN * nw;
+    constexpr int WIN = MLM_WIN;
+    constexpr int NT = 6144 / WIN, NP = WIN * NT;
+    const int nw = (K + WIN - 1) / WIN;
     MlmTables mt;
     {
         auto it = ctx->mlm.find(K);
         if (it == ctx->mlm.end()) {
             std::vector<uint16_t> pi(K);
             LTE_CUDA_OK(ctx, cudaMemcpy(pi.data(), qt.pi, K * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-            auto pos = [&](int k) { return (uint16_t)((k & 31) * nw + (k >> 5)); };
-            std::vector<uint16_t> piT(NP, 0), cs(K + 1, 0), cp(K);
+            auto pos = [&](int k) { return (uint16_t)((k % WIN) * NT + (k / WIN)); };
+            std::vector<uint16_t> piT(NP, 0), cs(NP + 1, 0), cp(K);
             for (int k = 0; k < K; k++) piT[pos(k)] = pos(pi[k]);
-            std::vector<int> cnt(K, 0);
-            for (int i = 0; i < K; i++) cnt[pi[i]]++;
-            for (int j = 0; j < K; j++) cs[j + 1] = (uint16_t)(cs[j] + cnt[j]);
+            std::vector<int> cnt(NP, 0);
+            for (int i = 0; i < K; i++) cnt[pos(pi[i])]++;
+            for (int q = 0; q < NP; q++) cs[q + 1] = (uint16_t)(cs[q] + cnt[q]);
             std::vector<int> fill(cs.begin(), cs.end() - 1);
-            for (int i = 0; i < K; i++) cp[fill[pi[i]]++] = pos(i);
+            for (int i = 0; i < K; i++) cp[fill[pos(pi[i])]++] = pos(i);   // increasing i inside each list
             LTE_CUDA_OK(ctx, cudaMalloc(&mt.piT, NP * 2));
-            LTE_CUDA_OK(ctx, cudaMalloc(&mt.csr_start, (K + 1) * 2));
+            LTE_CUDA_OK(ctx, cudaMalloc(&mt.csr_start, (NP + 1) * 2));
             LTE_CUDA_OK(ctx, cudaMalloc(&mt.csr_pos, K * 2));
             LTE_CUDA_OK(ctx, cudaMemcpy(mt.piT, piT.data(), NP * 2, cudaMemcpyHostToDevice));
-            LTE_CUDA_OK(ctx, cudaMemcpy(mt.csr_start, cs.data(), (K + 1) * 2, cudaMemcpyHostToDevice));
+            LTE_CUDA_OK(ctx, cudaMemcpy(mt.csr_start, cs.data(), (NP + 1) * 2, cudaMemcpyHostToDevice));
             LTE_CUDA_OK(ctx, cudaMemcpy(mt.csr_pos, cp.data(), K * 2, cudaMemcpyHostToDevice));
             ctx->mlm[K] = mt;
         } else mt = it->second;
     }
-    const size_t smem = (size_t)16 * NP + (size_t)4 * nw * 8 * 4 + (size_t)4 * NP * 2 + (size_t)4 * NP;
-    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)4 * NP * 2 + (size_t)(3 * NP + 2) * 2 + (size_t)3 * NP;
+    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = ((nw + 31) / 32) * 32;
-    turbo_mlm_kernel<<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits);
+    turbo_mlm_kernel<WIN><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;

@@ -98,4 +98,6 @@ def test_synthetic_cell_search_with_cfo_and_noise(ctx, port, refo):
         assert abs(th_p - r["pss_thresh"]) <= 1e-4 * th_p
         rc, ss_s, nid1_p, fsi_p = port.find_sss(i_s, q_s, fsi_, nrb, nid2_p, ss_p, th_p)
         assert rc == r["sss_rc"] == 0 and nid1_p == r["N_id_1"] == nid1 and fsi_p == r["frame_start_idx"]
-        assert r["N_id_2"] == nid2 and (r["frame_start_idx"] - off) % (10 * n_sf) == 0
+        # the reference places the frame start a few samples early (15 at 30.72 Msps on its own capture): allow that, modulo frames
+        d = (r["frame_start_idx"] - off) % (10 * n_sf)
+        assert r["N_id_2"] == nid2 and min(d, 10 * n_sf - d) <= 20

@@ -5,7 +5,8 @@ import numpy as np, torch
 import openlte_b200
 from oracle import port
 
-L = openlte_b200.load(); ctx = L.new_ctx(0)
+from openlte_b200.lib import Lib
+L = Lib(os.environ['LTEB200_SO']) if os.environ.get('LTEB200_SO') else openlte_b200.load(); ctx = L.new_ctx(0)
 K = 6144
 rng = np.random.default_rng(0)
 blocks = []
