@@ -184,53 +184,70 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     int16_t *Lsa2 = Lsa1 + NP, *Le1 = Lsa2 + NP, *Le2 = Le1 + NP;
     uint16_t *s_piT = (uint16_t *)(Le2 + NP);                       // interleaver and its CSR inverse, staged once per block
     uint16_t *s_cs = s_piT + NP, *s_cp = s_cs + (NP + 2);
-    int8_t *Ls = (int8_t *)(s_cp + NP);
+    int8_t *Ls = (int8_t *)(s_cp + NP + 2);
     int8_t *Lp1 = Ls + NP, *Lp2 = Lp1 + NP;
     __shared__ float s_red[32];
     __shared__ int s_tail[12];
 
     const int cb = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const float *d = llr + (size_t)cb * 3 * (K + 4);
-    // ---- max |d| over all 3(K+4) inputs (sentinel -> 0)
+    // ---- input: thread w owns steps 16w..16w+15 = 48 consecutive floats (192 B, 16-byte aligned), read once as float4.
+    // max |d| over all 3(K+4) inputs (sentinel -> 0) first, then quantisation straight from registers.
+    float v[3 * WIN];
     float m = 0.f;
-    for (int idx = tid; idx < 3 * (K + 4); idx += nt) {
-        float v = d[idx];
-        if (v == LTEB200_RX_NULL_BIT) v = 0.f;
-        m = fmaxf(m, fabsf(v));
+    const bool own = tid < nw;
+    const int nown = own ? min(WIN, K - WIN * tid) : 0;
+    if (nown == WIN) {
+        const float4 *src = reinterpret_cast<const float4 *>(d + 3 * WIN * tid);
+#pragma unroll
+        for (int j = 0; j < 3 * WIN / 4; j++) {
+            const float4 t = src[j];
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3 * WIN; j++) v[j] = (j < 3 * nown) ? d[3 * WIN * tid + j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 3 * WIN; j++) {
+        if (v[j] == LTEB200_RX_NULL_BIT) v[j] = 0.f;
+        m = fmaxf(m, fabsf(v[j]));
+    }
+    if (tid < 12) {                              // the 12 tail values take part in the maximum
+        float t = d[3 * K + tid];
+        if (t == LTEB200_RX_NULL_BIT) t = 0.f;
+        m = fmaxf(m, fabsf(t));
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) s_red[tid >> 5] = m;
     __syncthreads();
     if (tid < 32) {
-        float v = tid < (nt >> 5) ? s_red[tid] : 0.f;
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (tid == 0) s_red[0] = v;
+        float t = tid < (nt >> 5) ? s_red[tid] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (tid == 0) s_red[0] = t;
     }
     __syncthreads();
     const float maxv = s_red[0];
-    // ---- quantise into the transposed arrays; zero the padding
-    for (int p = tid; p < NP; p += nt) {
-        const int k = (p % NT) * WIN + (p / NT);
-        int q0 = 0, q1 = 0, q2 = 0;
-        if (k < K) {
-            float v0 = d[3 * k], v1 = d[3 * k + 1], v2 = d[3 * k + 2];
-            if (v0 == LTEB200_RX_NULL_BIT) v0 = 0.f;
-            if (v1 == LTEB200_RX_NULL_BIT) v1 = 0.f;
-            if (v2 == LTEB200_RX_NULL_BIT) v2 = 0.f;
-            q0 = qf(v0, maxv); q1 = qf(v1, maxv); q2 = qf(v2, maxv);
+    // ---- quantise into the window-transposed arrays (thread w writes column w: conflict free); padding stays zero
+    for (int p = tid; p < NP; p += nt) { Lsa2[p] = 0; Le1[p] = 0; Le2[p] = 0; }
+    if (tid < NT) {
+#pragma unroll
+        for (int i = 0; i < WIN; i++) {
+            const int p = i * NT + tid;
+            const int q0 = (i < nown) ? qf(v[3 * i], maxv) : 0, q1 = (i < nown) ? qf(v[3 * i + 1], maxv) : 0, q2 = (i < nown) ? qf(v[3 * i + 2], maxv) : 0;
+            Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2; Lsa1[p] = (int16_t)q0;
         }
-        Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2;
-        Lsa1[p] = (int16_t)q0; Lsa2[p] = 0; Le1[p] = 0; Le2[p] = 0;
     }
     if (tid < 12) {
-        float v = d[3 * K + tid];
-        if (v == LTEB200_RX_NULL_BIT) v = 0.f;
-        s_tail[tid] = qf(v, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
+        float tv = d[3 * K + tid];
+        if (tv == LTEB200_RX_NULL_BIT) tv = 0.f;
+        s_tail[tid] = qf(tv, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
     }
     for (int i = tid; i < NT * 4; i += nt) bA1[i] = make_uint4(0, 0, 0, 0);  // bA1,bB1,bA2,bB2 are contiguous
     for (int p = tid; p < NP; p += nt) s_piT[p] = piT[p];
     for (int j = tid; j <= NP; j += nt) s_cs[j] = csr_start[j];
-    for (int j = tid; j < K; j += nt) s_cp[j] = csr_pos[j];
+    for (int j = tid; j < NP; j += nt) s_cp[j] = j < K ? csr_pos[j] : (uint16_t)0;
+    if (tid < 2) s_cp[NP + tid] = 0;                                        // s_cp[t0+1], s_cp[t0+2] are read unconditionally
     __syncthreads();
 
     Pass P1, P2;
@@ -247,11 +264,16 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         for (int p = tid; p < NP; p += nt) { const int q = s_piT[p]; Lsa2[p] = (int16_t)((int)Ls[q] + (int)Le1[q]); }   // interleave
         __syncthreads();
         dec_pass<WIN, NT>(P2, tid, nw, K);
+#pragma unroll 4
         for (int p = tid; p < NP; p += nt) {                                                        // de-interleave, combine
-            int acc = 0;
-            const int e = s_cs[p + 1];
+            // 0..3 contributions per position for the reference's wrapped interleaver (exactly 1 for every spec-correct size):
+            // the first three are fetched unconditionally (independent loads), the rare rest in a loop
+            const int t0 = s_cs[p], cnt = (int)s_cs[p + 1] - t0;
+            const int i0 = s_cp[t0], i1 = s_cp[t0 + 1], i2 = s_cp[t0 + 2];
+            const int v0 = Le2[i0], v1 = Le2[i1], v2 = Le2[i2];
+            int acc = (cnt > 0 ? v0 : 0) + (cnt > 1 ? v1 : 0) + (cnt > 2 ? v2 : 0);
 #pragma unroll 1
-            for (int t = s_cs[p]; t < e; t++) acc += (int)Le2[s_cp[t]];   // 0..3 entries (1 for every spec-correct block size)
+            for (int t = t0 + 3; t < t0 + cnt; t++) acc += (int)Le2[s_cp[t]];
             Lsa1[p] = (int16_t)((int)Ls[p] + clampi(acc, -LA_LIM, LA_LIM));
         }
         __syncthreads();
@@ -297,7 +319,7 @@ int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
             ctx->mlm[K] = mt;
         } else mt = it->second;
     }
-    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)4 * NP * 2 + (size_t)(3 * NP + 2) * 2 + (size_t)3 * NP;
+    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)4 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
     LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = ((nw + 31) / 32) * 32;
     turbo_mlm_kernel<WIN><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits);
