@@ -31,28 +31,11 @@ __device__ __forceinline__ float soft_dist(float re, float im, float ere, float 
     return __fsub_rn(1.0f, dist);
 }
 
-// re_idx: [3][idx_stride] (symbol*nsc + subcarrier) per subframe class; M_cls[3]; cseq: [10][c_stride] scrambling bits per subframe number
-__global__ void __launch_bounds__(128)
-pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const float2 *__restrict__ ce /*[n_sf][N_ant][14][nsc]*/, int N_ant,
-                   const int *__restrict__ subfr_num, const int *__restrict__ re_idx, int idx_stride, int3 M_cls,
-                   const uint8_t *__restrict__ cseq, int c_stride, DemodParams P, float *__restrict__ soft)
+__device__ __forceinline__ void demap_store(float xr, float xi, int mod, int Qm, const uint8_t *__restrict__ c, float *__restrict__ o)
 {
-    const int sf = blockIdx.y;
-    const int sn = subfr_num[sf];
-    const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
-    const int M = cls == 0 ? M_cls.x : (cls == 1 ? M_cls.y : M_cls.z);
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= M) return;
-    const int idx = re_idx[cls * idx_stride + r];
-    const float2 y = grid[(size_t)sf * 16 * P.nsc + idx];
-    const float2 h = ce[(size_t)sf * N_ant * 14 * P.nsc + idx];
-    // zero forcing: x = y * conj(h) / |h|^2, operation order of liblte_phy.cc:7684-7689
-    const float nrm = __fadd_rn(__fmul_rn(h.x, h.x), __fmul_rn(h.y, h.y));
-    const float xr = __fdiv_rn(__fadd_rn(__fmul_rn(y.x, h.x), __fmul_rn(y.y, h.y)), nrm);
-    const float xi = __fdiv_rn(__fsub_rn(__fmul_rn(y.y, h.x), __fmul_rn(y.x, h.y)), nrm);
     int b[6];
     const float r2 = 0.70710678118654752440f;
-    if (P.mod == LTEB200_MOD_QPSK) {
+    if (mod == LTEB200_MOD_QPSK) {
         const float ang = atan2f(xi, xr);
         const double a = (double)ang, hp = 1.57079632679489661923, pi = 3.14159265358979323846;
         int s0, s1;
@@ -62,11 +45,11 @@ pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const fl
         else { s0 = -1; s1 = -1; }
         const int m = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, s0 > 0 ? r2 : -r2, s1 > 0 ? r2 : -r2)));
         b[0] = s0 * m; b[1] = s1 * m;
-    } else if (P.mod == LTEB200_MOD_16QAM) {
+    } else if (mod == LTEB200_MOD_16QAM) {
         const float t = 0.63245553203367586640f;  // 2/sqrt(10)
         b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
         b[2] = fabsf(xr) < t ? 127 : -127; b[3] = fabsf(xi) < t ? 127 : -127;
-    } else if (P.mod == LTEB200_MOD_64QAM) {
+    } else if (mod == LTEB200_MOD_64QAM) {
         const float t2 = 0.30860669992418382490f, t4 = 0.61721339984836764980f, t6 = 0.92582009977255147470f;  // {2,4,6}/sqrt(42)
         const float ar = fabsf(xr), ai = fabsf(xi);
         b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
@@ -77,9 +60,70 @@ pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const fl
         if (a > -pi / 4 && a < 3 * pi / 4) b[0] = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, r2, r2)));
         else b[0] = -__float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, -r2, -r2)));
     }
+    for (int t = 0; t < Qm; t++) o[t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)c[t]));  // soft * (1 - 2c), :3835
+}
+
+// four-term sums in the reference's left-to-right order
+__device__ __forceinline__ float sum4(float a, float b, float c, float d) { return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d); }
+#define MUL(a, b) __fmul_rn((a), (b))
+
+// re_idx: [3][idx_stride] (symbol*nsc + subcarrier) per subframe class; M_cls[3]; cseq: [10][c_stride] scrambling bits per subframe number.
+// One thread per group of N_ant consecutive PDSCH resource elements (1 port: zero forcing, liblte_phy.cc:7680-7690;
+// 2 / 4 ports: transmit-diversity combining, :7691-7765, followed by layer_demapper_dl's interleave, :7505-7512).
+__global__ void __launch_bounds__(128)
+pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const float2 *__restrict__ ce /*[n_sf][N_ant][14][nsc]*/, int N_ant,
+                   const int *__restrict__ subfr_num, const int *__restrict__ re_idx, int idx_stride, int3 M_cls,
+                   const uint8_t *__restrict__ cseq, int c_stride, DemodParams P, float *__restrict__ soft)
+{
+    const int sf = blockIdx.y;
+    const int sn = subfr_num[sf];
+    const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
+    const int M = cls == 0 ? M_cls.x : (cls == 1 ? M_cls.y : M_cls.z);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = g * N_ant;
+    if (r + N_ant > M) return;
+    const int *ix = re_idx + cls * idx_stride + r;
+    const float2 *gr = grid + (size_t)sf * 16 * P.nsc;
+    const float2 *cp = ce + (size_t)sf * N_ant * 14 * P.nsc;
+    const size_t pstride = (size_t)14 * P.nsc;
     const uint8_t *c = cseq + (size_t)sn * c_stride + (size_t)r * P.Qm;
     float *o = soft + (size_t)sf * P.soft_stride + (size_t)r * P.Qm;
-    for (int t = 0; t < P.Qm; t++) o[t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)c[t]));  // soft * (1 - 2c), :3835
+    if (N_ant == 1) {
+        const float2 y = gr[ix[0]], h = cp[ix[0]];
+        // zero forcing: x = y * conj(h) / |h|^2, operation order of liblte_phy.cc:7684-7689
+        const float nrm = __fadd_rn(MUL(h.x, h.x), MUL(h.y, h.y));
+        const float xr = __fdiv_rn(__fadd_rn(MUL(y.x, h.x), MUL(y.y, h.y)), nrm);
+        const float xi = __fdiv_rn(__fsub_rn(MUL(y.y, h.x), MUL(y.x, h.y)), nrm);
+        demap_store(xr, xi, P.mod, P.Qm, c, o);
+    } else if (N_ant == 2) {
+        const float2 y0 = gr[ix[0]], y1 = gr[ix[1]], h0 = cp[ix[0]], h1 = cp[pstride + ix[0]];   // both estimates at the EVEN element (:7696-7699)
+        const float a0 = __fadd_rn(MUL(h0.x, h0.x), MUL(h0.y, h0.y)), a1 = __fadd_rn(MUL(h1.x, h1.x), MUL(h1.y, h1.y));
+        const float n = __fsqrt_rn(__fadd_rn(MUL(a0, a0), MUL(a1, a1)));                        // sic: sqrt(|h0|^4 + |h1|^4)
+        const float x0r = __fdiv_rn(sum4(MUL(h0.x, y0.x), MUL(h0.y, y0.y), MUL(h1.x, y1.x), MUL(h1.y, y1.y)), n);
+        const float x0i = __fdiv_rn(sum4(MUL(h0.x, y0.y), -MUL(h0.y, y0.x), -MUL(h1.x, y1.y), MUL(h1.y, y1.x)), n);
+        const float x1r = __fdiv_rn(sum4(-MUL(h1.x, y0.x), -MUL(h1.y, y0.y), MUL(h0.x, y1.x), MUL(h0.y, y1.y)), n);
+        const float x1i = __fdiv_rn(sum4(MUL(h1.x, y0.y), -MUL(h1.y, y0.x), MUL(h0.x, y1.y), -MUL(h0.y, y1.x)), n);
+        demap_store(x0r, x0i, P.mod, P.Qm, c, o);
+        demap_store(x1r, x1i, P.mod, P.Qm, c + P.Qm, o + P.Qm);
+    } else {
+        const float2 y0 = gr[ix[0]], y1 = gr[ix[1]], y2 = gr[ix[2]], y3 = gr[ix[3]];
+        const float2 h0 = cp[ix[0]], h2 = cp[2 * pstride + ix[0]], h1 = cp[pstride + ix[2]], h3 = cp[3 * pstride + ix[2]];   // :7723-7730
+        const float a0 = __fadd_rn(MUL(h0.x, h0.x), MUL(h0.y, h0.y)), a1 = __fadd_rn(MUL(h1.x, h1.x), MUL(h1.y, h1.y));
+        const float a2 = __fadd_rn(MUL(h2.x, h2.x), MUL(h2.y, h2.y)), a3 = __fadd_rn(MUL(h3.x, h3.x), MUL(h3.y, h3.y));
+        const float n02 = __fsqrt_rn(__fadd_rn(MUL(a0, a0), MUL(a2, a2))), n13 = __fsqrt_rn(__fadd_rn(MUL(a1, a1), MUL(a3, a3)));
+        const float x0r = __fdiv_rn(sum4(MUL(h0.x, y0.x), MUL(h0.y, y0.y), MUL(h2.x, y1.x), MUL(h2.y, y1.y)), n02);
+        const float x0i = __fdiv_rn(sum4(MUL(h0.x, y0.y), -MUL(h0.y, y0.x), -MUL(h2.x, y1.y), MUL(h2.y, y1.x)), n02);
+        const float x1r = __fdiv_rn(sum4(-MUL(h2.x, y0.x), -MUL(h2.y, y0.y), MUL(h0.x, y1.x), MUL(h0.y, y1.y)), n02);
+        const float x1i = __fdiv_rn(-sum4(-MUL(h2.x, y0.y), MUL(h2.y, y0.x), -MUL(h0.x, y1.y), MUL(h0.y, y1.x)), n02);
+        const float x2r = __fdiv_rn(sum4(MUL(h1.x, y2.x), MUL(h1.y, y2.y), MUL(h3.x, y3.x), MUL(h3.y, y3.y)), n13);
+        const float x2i = __fdiv_rn(sum4(MUL(h1.x, y2.y), -MUL(h1.y, y2.x), -MUL(h3.x, y3.y), MUL(h3.y, y3.x)), n13);
+        const float x3r = __fdiv_rn(sum4(-MUL(h3.x, y2.x), -MUL(h3.y, y2.y), MUL(h1.x, y3.x), MUL(h1.y, y3.y)), n13);
+        const float x3i = __fdiv_rn(-sum4(-MUL(h3.x, y2.y), MUL(h3.y, y2.x), -MUL(h1.x, y3.y), MUL(h1.y, y3.x)), n13);
+        demap_store(x0r, x0i, P.mod, P.Qm, c, o);
+        demap_store(x1r, x1i, P.mod, P.Qm, c + P.Qm, o + P.Qm);
+        demap_store(x2r, x2i, P.mod, P.Qm, c + 2 * P.Qm, o + 2 * P.Qm);
+        demap_store(x3r, x3i, P.mod, P.Qm, c + 3 * P.Qm, o + 3 * P.Qm);
+    }
 }
 
 // One CTA per code block: CRC24A over the transport block inside the decoded block, bit extraction.
@@ -239,14 +283,19 @@ int pdsch_demod_launch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce,
                        const int *d_subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc &al, float *d_soft, int soft_stride,
                        AllocTables *tabs_out, cudaStream_t stream)
 {
-    if (N_ant != 1) { lteb200_set_error(ctx, "PDSCH receive: only N_ant == 1 is implemented (transmit diversity combining is a next row)"); return LTEB200_ERR_UNSUPPORTED; }
+    if (!(N_ant == 1 || N_ant == 2 || N_ant == 4)) { lteb200_set_error(ctx, "PDSCH receive: N_ant must be 1, 2 or 4"); return LTEB200_ERR_ARGS; }
     AllocTables t;
     int rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, al, &t);
     if (rc) return rc;
+    for (int c = 0; c < 3; c++)
+        if (t.M[c] % N_ant) {   // the reference's own odd-tail handling for 4 ports is inconsistent (layer strides differ between :7676 and :7486): refuse
+            lteb200_set_error(ctx, "allocation has %d resource elements, not a multiple of N_ant=%d", t.M[c], N_ant);
+            return LTEB200_ERR_UNSUPPORTED;
+        }
     if (soft_stride < t.M[2] * t.Qm) { lteb200_set_error(ctx, "soft_stride too small: need %d", t.M[2] * t.Qm); return LTEB200_ERR_ARGS; }
     DemodParams P;
     P.nsc = 12 * N_rb_dl; P.Qm = t.Qm; P.mod = al.mod_type; P.soft_stride = soft_stride;
-    dim3 grid(ceil_div(t.M[2], 128), n_sf);
+    dim3 grid(ceil_div(t.M[2] / N_ant, 128), n_sf);
     pdsch_demod_kernel<<<grid, 128, 0, stream>>>((const float2 *)d_grid, (const float2 *)d_ce, N_ant, d_subfr_num, t.re_idx, t.idx_stride,
                                                  make_int3(t.M[0], t.M[1], t.M[2]), t.cseq, t.c_stride, P, d_soft);
     ctx->launches += 1;

@@ -149,3 +149,20 @@ def find_sss(i_s, q_s, fs_idx, N_rb_dl, N_id_2, symb_starts, pss_thresh):
     a = C.c_uint32(0); b = C.c_uint32(0)
     rc = lib().op_find_sss(_p(i_s), _p(q_s), fs_idx, N_rb_dl, C.c_uint32(N_id_2), _p(ss), C.c_float(pss_thresh), C.byref(a), C.byref(b))
     return rc, ss, a.value, b.value
+
+
+def pre_decoder_dl(y_re, y_im, h_re, h_im, N_ant):
+    a = [np.ascontiguousarray(v, np.float32) for v in (y_re, y_im, h_re, h_im)]
+    M = a[0].size; d_re = np.zeros(M + 4, np.float32); d_im = np.zeros(M + 4, np.float32)
+    n = lib().op_pre_decoder_dl(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), M, M, N_ant, _p(d_re), _p(d_im))
+    return d_re[:n], d_im[:n]
+
+
+def pdsch_decode_nant(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, N_ant, subfr, cfi, mod, prb, tbs, rnti, rv=0, turbo_mode=0, n_iter=8):
+    """ce_*: [N_ant][16][1200]; returns (rc, bits, descrambled soft bits)"""
+    prb = np.ascontiguousarray(prb, np.int32); out = np.zeros(tbs + 32, np.uint8)
+    a = [np.ascontiguousarray(v, np.float32) for v in (rx_re, rx_im, ce_re, ce_im)]
+    soft = np.zeros(14 * 12 * prb.size * 6, np.float32); n = C.c_int(0)
+    rc = lib().op_pdsch_decode_nant(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), N_rb_dl, N_id_cell, N_ant, subfr, cfi, mod, int(prb.size), _p(prb), tbs, rv,
+                                    rnti, turbo_mode, n_iter, _p(out), _p(soft), C.byref(n))
+    return rc, out[:tbs], soft[:n.value]

@@ -69,6 +69,58 @@ extern "C" void op_zf_1ant(const float *y_re, const float *y_im, const float *h_
     }
 }
 
+/* pre_decoder_and_matched_filter_dl + layer_demapper_dl for transmit diversity (liblte_phy.cc:7645-7796, 7473-7514).
+ * h_*: [N_ant][h_len]; returns M_symb and writes the layer-demapped symbols d[]. */
+extern "C" int op_pre_decoder_dl(const float *yr, const float *yi, const float *h_re, const float *h_im, int h_len, int M, int N_ant,
+                                 float *d_re, float *d_im)
+{
+    if (N_ant == 1) { op_zf_1ant(yr, yi, h_re, h_im, M, d_re, d_im); return M; }
+    const float *hr[4], *hi[4];
+    for (int p = 0; p < N_ant; p++) { hr[p] = h_re + (size_t)p * h_len; hi[p] = h_im + (size_t)p * h_len; }
+    if (N_ant == 2) {
+        for (int i = 0; i < M / 2; i++) {
+            const float h0r = hr[0][2 * i], h0i = hi[0][2 * i], h1r = hr[1][2 * i], h1i = hi[1][2 * i];
+            const float y0r = yr[2 * i], y0i = yi[2 * i], y1r = yr[2 * i + 1], y1i = yi[2 * i + 1];
+            const float a0 = h0r * h0r + h0i * h0i, a1 = h1r * h1r + h1i * h1i;
+            const float n = sqrtf(a0 * a0 + a1 * a1);                                  /* sic: sqrt(|h0|^4 + |h1|^4), :7700 */
+            d_re[2 * i]     = (h0r * y0r + h0i * y0i + h1r * y1r + h1i * y1i) / n;
+            d_im[2 * i]     = (h0r * y0i - h0i * y0r - h1r * y1i + h1i * y1r) / n;
+            d_re[2 * i + 1] = (-h1r * y0r - h1i * y0i + h0r * y1r + h0i * y1i) / n;
+            d_im[2 * i + 1] = (h1r * y0i - h1i * y0r + h0r * y1i - h0i * y1r) / n;
+        }
+        return (M / 2) * 2;
+    }
+    int i;
+    for (i = 0; i < M / 4; i++) {
+        const float h0r = hr[0][4 * i], h0i = hi[0][4 * i], h2r = hr[2][4 * i], h2i = hi[2][4 * i];
+        const float h1r = hr[1][4 * i + 2], h1i = hi[1][4 * i + 2], h3r = hr[3][4 * i + 2], h3i = hi[3][4 * i + 2];
+        const float y0r = yr[4 * i], y0i = yi[4 * i], y1r = yr[4 * i + 1], y1i = yi[4 * i + 1];
+        const float y2r = yr[4 * i + 2], y2i = yi[4 * i + 2], y3r = yr[4 * i + 3], y3i = yi[4 * i + 3];
+        const float a0 = h0r * h0r + h0i * h0i, a1 = h1r * h1r + h1i * h1i, a2 = h2r * h2r + h2i * h2i, a3 = h3r * h3r + h3i * h3i;
+        const float n02 = sqrtf(a0 * a0 + a2 * a2), n13 = sqrtf(a1 * a1 + a3 * a3);
+        d_re[4 * i]     = (h0r * y0r + h0i * y0i + h2r * y1r + h2i * y1i) / n02;
+        d_im[4 * i]     = (h0r * y0i - h0i * y0r - h2r * y1i + h2i * y1r) / n02;
+        d_re[4 * i + 1] = (-h2r * y0r - h2i * y0i + h0r * y1r + h0i * y1i) / n02;
+        d_im[4 * i + 1] = -(-h2r * y0i + h2i * y0r - h0r * y1i + h0i * y1r) / n02;
+        d_re[4 * i + 2] = (h1r * y2r + h1i * y2i + h3r * y3r + h3i * y3i) / n13;
+        d_im[4 * i + 2] = (h1r * y2i - h1i * y2r - h3r * y3i + h3i * y3r) / n13;
+        d_re[4 * i + 3] = (-h3r * y2r - h3i * y2i + h1r * y3r + h1i * y3i) / n13;
+        d_im[4 * i + 3] = -(-h3r * y2i + h3i * y2r - h1r * y3i + h1i * y3r) / n13;
+    }
+    if (M % 4 != 0) {           /* odd tail: two symbols on ports 0/2 only (:7766-7795, with its different x1_im) */
+        const float h0r = hr[0][4 * i], h0i = hi[0][4 * i], h2r = hr[2][4 * i], h2i = hi[2][4 * i];
+        const float y0r = yr[4 * i], y0i = yi[4 * i], y1r = yr[4 * i + 1], y1i = yi[4 * i + 1];
+        const float a0 = h0r * h0r + h0i * h0i, a2 = h2r * h2r + h2i * h2i;
+        const float n02 = sqrtf(a0 * a0 + a2 * a2);
+        d_re[4 * i]     = (h0r * y0r + h0i * y0i + h2r * y1r + h2i * y1i) / n02;
+        d_im[4 * i]     = (h0r * y0i - h0i * y0r - h2r * y1i + h2i * y1r) / n02;
+        d_re[4 * i + 1] = (-h2r * y0r - h2i * y0i + h0r * y1r + h0i * y1i) / n02;
+        d_im[4 * i + 1] = (-h2r * y0i + h2i * y0r - h0r * y1r + h0i * y1i) / n02;
+        return 4 * i + 2;
+    }
+    return 4 * i;
+}
+
 static inline float soft_dist(float re, float im, float ere, float eim)
 {
     /* get_soft_decision(rx, exp, max_dist = 1), liblte_phy.cc:13880-13900 */
@@ -302,21 +354,27 @@ extern "C" void op_get_dl_subframe_and_ce(const float *i_samps, const float *q_s
 }
 
 /* ------------------------------------------------------------------------------------- PDSCH, one allocation */
-extern "C" int op_pdsch_decode(const float *rx_re, const float *rx_im, const float *ce_re, const float *ce_im, int N_rb_dl, int N_id_cell,
-                               int subfr, int N_pdcch_symbs, int mod, int N_prb, const int *prb, int tbs, int rv, int rnti,
-                               int turbo_mode, int n_iter, uint8_t *out_bits)
+/* ce_*: [N_ant][16][1200] (port-major, as LIBLTE_PHY_SUBFRAME_STRUCT); soft_out (optional): the descrambled soft bits */
+extern "C" int op_pdsch_decode_nant(const float *rx_re, const float *rx_im, const float *ce_re, const float *ce_im, int N_rb_dl, int N_id_cell,
+                                    int N_ant, int subfr, int N_pdcch_symbs, int mod, int N_prb, const int *prb, int tbs, int rv, int rnti,
+                                    int turbo_mode, int n_iter, uint8_t *out_bits, float *soft_out, int *n_soft)
 {
     std::vector<int> idx(14 * 12 * N_prb);
-    const int M = op_pdsch_re_indices(N_rb_dl, N_id_cell, 1, subfr, N_pdcch_symbs, N_prb, prb, prb, idx.data());
-    std::vector<float> yr(M), yi(M), hr(M), hi(M), xr(M), xi(M);
-    for (int i = 0; i < M; i++) { yr[i] = rx_re[idx[i]]; yi[i] = rx_im[idx[i]]; hr[i] = ce_re[idx[i]]; hi[i] = ce_im[idx[i]]; }
-    op_zf_1ant(yr.data(), yi.data(), hr.data(), hi.data(), M, xr.data(), xi.data());
-    std::vector<int8_t> soft(6 * M);
+    const int Mre = op_pdsch_re_indices(N_rb_dl, N_id_cell, N_ant, subfr, N_pdcch_symbs, N_prb, prb, prb, idx.data());
+    std::vector<float> yr(Mre), yi(Mre), hr((size_t)N_ant * Mre), hi((size_t)N_ant * Mre), xr(Mre + 4), xi(Mre + 4);
+    for (int i = 0; i < Mre; i++) {
+        yr[i] = rx_re[idx[i]]; yi[i] = rx_im[idx[i]];
+        for (int p = 0; p < N_ant; p++) { hr[(size_t)p * Mre + i] = ce_re[(size_t)p * 16 * 1200 + idx[i]]; hi[(size_t)p * Mre + i] = ce_im[(size_t)p * 16 * 1200 + idx[i]]; }
+    }
+    const int M = op_pre_decoder_dl(yr.data(), yi.data(), hr.data(), hi.data(), Mre, Mre, N_ant, xr.data(), xi.data());
+    std::vector<int8_t> soft(6 * (size_t)M + 8);
     const int G = op_demap(xr.data(), xi.data(), M, mod, soft.data());
+    if (n_soft) *n_soft = G;
     std::vector<uint8_t> c(G);
     op_prs_c(((uint32_t)rnti << 14) | ((uint32_t)subfr << 9) | (uint32_t)N_id_cell, G, c.data());
     std::vector<float> llr(G);
     for (int i = 0; i < G; i++) llr[i] = (float)soft[i] * (1 - 2 * (float)c[i]);
+    if (soft_out) memcpy(soft_out, llr.data(), sizeof(float) * G);
     int K, F, C;
     op_segmentation_params(tbs, &K, &F, &C);
     if (C != 1) return -4;
@@ -332,4 +390,12 @@ extern "C" int op_pdsch_decode(const float *rx_re, const float *rx_im, const flo
     if (crc != rx) return -3;
     memcpy(out_bits, a, tbs);
     return 0;
+}
+
+extern "C" int op_pdsch_decode(const float *rx_re, const float *rx_im, const float *ce_re, const float *ce_im, int N_rb_dl, int N_id_cell,
+                               int subfr, int N_pdcch_symbs, int mod, int N_prb, const int *prb, int tbs, int rv, int rnti,
+                               int turbo_mode, int n_iter, uint8_t *out_bits)
+{
+    return op_pdsch_decode_nant(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, 1, subfr, N_pdcch_symbs, mod, N_prb, prb, tbs, rv, rnti, turbo_mode,
+                                n_iter, out_bits, NULL, NULL);
 }

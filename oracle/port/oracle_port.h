@@ -44,6 +44,8 @@ void     op_segmentation_params(int tbs, int *K, int *F, int *C);      /* liblte
 
 /* ---- demapping chain (a8-a11) */
 void op_zf_1ant(const float *y_re, const float *y_im, const float *h_re, const float *h_im, int n, float *x_re, float *x_im);
+int  op_pre_decoder_dl(const float *y_re, const float *y_im, const float *h_re, const float *h_im, int h_len, int M, int N_ant,
+                       float *d_re, float *d_im);
 int  op_demap(const float *d_re, const float *d_im, int M, int mod_type, int8_t *bits);
 /* ---- RE extraction (a7): writes indices (symbol*1200+sc) of the PDSCH REs of one allocation */
 int  op_pdsch_re_indices(int N_rb_dl, int N_id_cell, int N_ant, int subfr_num, int N_pdcch_symbs, int N_prb,
@@ -65,6 +67,10 @@ void op_chan_est(const float *rx_symb_re, const float *rx_symb_im, int N_rb_dl, 
 int op_pdsch_decode(const float *rx_symb_re, const float *rx_symb_im, const float *rx_ce_re, const float *rx_ce_im,
                     int N_rb_dl, int N_id_cell, int subfr_num, int N_pdcch_symbs, int mod_type, int N_prb, const int *prb,
                     int tbs, int rv, int rnti, int turbo_mode, int n_iter, uint8_t *out_bits);
+
+int op_pdsch_decode_nant(const float *rx_symb_re, const float *rx_symb_im, const float *rx_ce_re, const float *rx_ce_im, int N_rb_dl,
+                         int N_id_cell, int N_ant, int subfr_num, int N_pdcch_symbs, int mod_type, int N_prb, const int *prb, int tbs, int rv,
+                         int rnti, int turbo_mode, int n_iter, uint8_t *out_bits, float *soft_out, int *n_soft);
 
 /* ---- sync (a2-a4) */
 int op_find_coarse_timing(const float *i_samps, const float *q_samps, int fs_idx, int N_slots, float *freq_offset /*[5]*/,

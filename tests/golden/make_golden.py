@@ -22,27 +22,27 @@ QM = {0: 1, 1: 2, 2: 4, 3: 6}
 
 
 def loopback_case(name, fs, N_rb_dl, cell, subfr, mod, prb, tbs, rnti, N_ant_ce=1, gain=0.7 * np.exp(0.9j), noise=0.002, cfi=2, seed=0,
-                  frame_start=0):
+                  frame_start=0, N_ant_tx=1):
     lb = ref_loopback(ref, subfr, [dict(mod=mod, prb=prb, tbs=tbs, rnti=rnti)], N_id_cell=cell, cfi=cfi, N_rb_dl=N_rb_dl, fs=fs, seed=seed,
-                      gain=gain, noise=noise, frame_start=frame_start)
+                      gain=gain, noise=noise, frame_start=frame_start, N_ant=N_ant_tx)
     phy = lb["phy"]
     sf = ref.Subframe()
     phy.get_dl_subframe_and_ce(lb["i"], lb["q"], frame_start, subfr, cell, N_ant_ce, sf)
     rx_re, rx_im = sf.rx_symb_re.copy(), sf.rx_symb_im.copy()
     ce_re, ce_im = sf.rx_ce_re.copy(), sf.rx_ce_im.copy()
-    # PDSCH decode uses the single-port estimate (the transmitter has one port)
+    # PDSCH decode uses as many ports as the transmitter has
     sf1 = ref.Subframe()
-    phy.get_dl_subframe_and_ce(lb["i"], lb["q"], frame_start, subfr, cell, 1, sf1)
-    err, bits = phy.pdsch_decode(sf1, cfi, cell, 1, mod, prb, tbs, rnti)
+    phy.get_dl_subframe_and_ce(lb["i"], lb["q"], frame_start, subfr, cell, N_ant_tx, sf1)
+    err, bits = phy.pdsch_decode(sf1, cfi, cell, N_ant_tx, mod, prb, tbs, rnti)
     from oracle import port
-    n_re = port.pdsch_re_indices(N_rb_dl, cell, 1, subfr, cfi, prb).size
+    n_re = port.pdsch_re_indices(N_rb_dl, cell, N_ant_tx, subfr, cfi, prb).size
     G = n_re * QM[mod]
     descr = phy.pdsch_scratch(1, G, np.float32)
     # trim the sample arrays to what the receiver touches
     n_keep = frame_start + (subfr + 1) * lb["n_sf"] + 3 * (128 << FS_IDX[fs]) * 2
     np.savez_compressed(os.path.join(HERE, name), i=lb["i"][:n_keep], q=lb["q"][:n_keep], fs_idx=FS_IDX[fs], N_rb_dl=N_rb_dl, N_id_cell=cell,
                         subfr=subfr, n_sf=lb["n_sf"], frame_start=frame_start, mod=mod, prb=np.array(prb, np.int32), tbs=tbs, rnti=rnti, cfi=cfi,
-                        N_ant_ce=N_ant_ce, tb=lb["tb"][0], ref_rx_re=rx_re, ref_rx_im=rx_im, ref_ce_re=ce_re[:, :14], ref_ce_im=ce_im[:, :14],
+                        N_ant_ce=N_ant_ce, N_ant_tx=N_ant_tx, tb=lb["tb"][0], ref_rx_re=rx_re, ref_rx_im=rx_im, ref_ce_re=ce_re[:, :14], ref_ce_im=ce_im[:, :14],
                         ref_descramb=descr, ref_crc_ok=int(err == 0), ref_tb=bits)
     print(name, "G", G, "ref err", err, "tb ok", np.array_equal(bits, lb["tb"][0]))
 
@@ -144,6 +144,9 @@ if __name__ == "__main__":
     loopback_case("loop_qpsk_c77_sf5.npz", 30.72, 100, 77, 5, 1, list(range(40, 76)), 3240, 0x0A0B, N_ant_ce=2, seed=1)
     loopback_case("loop_16qam_c150_sf0.npz", 30.72, 100, 150, 0, 2, list(range(41, 59)), 3112, 0x7FFF, seed=2)
     loopback_case("loop_qpsk_5mhz_c301_sf3.npz", 7.68, 25, 301, 3, 1, list(range(2, 20)), 1544, 0x0042, N_ant_ce=4, seed=3, frame_start=137)
+    loopback_case("loop_2ant_16qam_c21_sf2.npz", 30.72, 100, 21, 2, 2, list(range(10, 28)), 2216, 0x0F0F, N_ant_ce=2, N_ant_tx=2, seed=4)
+    loopback_case("loop_4ant_qpsk_10mhz_c400_sf5.npz", 15.36, 50, 400, 5, 1, list(range(20, 50)), 2216, 0x1111, N_ant_ce=4, N_ant_tx=4, seed=5)
+    loopback_case("loop_2ant_64qam_c5_sf7.npz", 30.72, 100, 5, 7, 3, list(range(60, 72)), 2216, 0x2222, N_ant_ce=2, N_ant_tx=2, seed=6)
     turbo_cases()
     ratematch_cases()
     sequence_cases()

@@ -21,7 +21,8 @@ def _loopback_case(name):
     return {k: z[k] for k in z.files}
 
 
-CASES = ["loop_64qam_c0_sf1.npz", "loop_qpsk_c77_sf5.npz", "loop_16qam_c150_sf0.npz", "loop_qpsk_5mhz_c301_sf3.npz"]
+CASES = ["loop_64qam_c0_sf1.npz", "loop_qpsk_c77_sf5.npz", "loop_16qam_c150_sf0.npz", "loop_qpsk_5mhz_c301_sf3.npz",
+         "loop_2ant_16qam_c21_sf2.npz", "loop_4ant_qpsk_10mhz_c400_sf5.npz", "loop_2ant_64qam_c5_sf7.npz"]
 
 
 def gpu_front(ctx, case):
@@ -58,13 +59,15 @@ def test_ofdm_and_ce_against_oracle(ctx, port, name):
     want_c = (ce_re + 1j * ce_im)[:n_ant, :14, :nsc]
     ref_c = (case["ref_ce_re"] + 1j * case["ref_ce_im"])[:n_ant, :14, :nsc]
     cs = np.abs(want_c[0]).max()
-    # Port 0 carries the transmitted CRS.  Stated tolerance 1e-4 of the estimate's maximum: atan2f/cosf/sinf differ from
+    n_tx = int(case["N_ant_tx"]) if "N_ant_tx" in case else 1
+    # Ports below n_tx carry a transmitted CRS.  Stated tolerance 1e-4 of the estimate's maximum: atan2f/cosf/sinf differ from
     # glibc by 1-2 ulp and unwrapped angles reach tens of radians.
-    assert np.abs(c[0] - want_c[0]).max() <= 1e-4 * cs, "channel estimate (port 0): relative error above 1e-4"
-    assert np.abs(c[0] - ref_c[0]).max() <= 1e-4 * cs
+    for p_ in range(n_tx):
+        assert np.abs(c[p_] - want_c[p_]).max() <= 1e-4 * cs, "channel estimate (transmitted port): relative error above 1e-4"
+        assert np.abs(c[p_] - ref_c[p_]).max() <= 1e-4 * cs
     # The fixtures transmit on one port only; estimating ports 1-3 there means unwrapping the phase of data/noise, which is
     # chaotic (a 1e-7 perturbation of the grid can move an interpolated value): require agreement on 99.5 % of the elements.
-    for p_ in range(1, n_ant):
+    for p_ in range(n_tx, n_ant):
         frac_ok = (np.abs(c[p_] - want_c[p_]) <= 1e-3 * cs).mean()
         assert frac_ok >= 0.995, (p_, frac_ok)
 
@@ -93,13 +96,16 @@ def test_pdsch_soft_bits_and_decode(ctx, port, name):
     import torch
     case = _loopback_case(name)
     nsc = 12 * int(case["N_rb_dl"])
+    n_tx = int(case["N_ant_tx"]) if "N_ant_tx" in case else 1
+    if n_tx > 1:
+        assert int(case["N_ant_ce"]) == n_tx
     _, _, grid, ce = gpu_front(ctx, case)
     al = Alloc.make(int(case["mod"]), [int(x) for x in case["prb"]], int(case["tbs"]), int(case["rnti"]))
     sn = np.array([int(case["subfr"])], np.int32)
     # ---- stage parity: descrambled soft bits
     stride = 14 * 12 * len(case["prb"]) * 6
     soft = torch.zeros((1, stride), dtype=torch.float32, device="cuda"); nb = np.zeros(1, np.int32)
-    ctx.check(ctx.lib.pdsch_demod_batch(ctx.h, dptr(grid), dptr(ce), int(case["N_rb_dl"]), int(case["N_id_cell"]), 1,
+    ctx.check(ctx.lib.pdsch_demod_batch(ctx.h, dptr(grid), dptr(ce), int(case["N_rb_dl"]), int(case["N_id_cell"]), n_tx,
                                         sn.ctypes.data_as(C.c_void_p), 1, int(case["cfi"]), C.byref(al), dptr(soft), stride,
                                         nb.ctypes.data_as(C.c_void_p), stream_ptr()))
     torch.cuda.synchronize()
@@ -107,14 +113,14 @@ def test_pdsch_soft_bits_and_decode(ctx, port, name):
     want = case["ref_descramb"]
     assert nb[0] == want.size
     if int(case["mod"]) >= 2:
-        assert np.array_equal(got, want), "hard-decision soft bits must match the reference exactly"
+        assert (got != want).mean() <= (0.0 if n_tx == 1 else 1e-3), "hard-decision soft bits must match the reference"
     else:
         assert np.abs(got - want).max() <= 1.0, "QPSK soft bits: +-1 LSB (atan2f / FFT ulp differences)"
         assert (np.sign(got) == np.sign(want)).mean() > 0.9999
     # ---- end to end: transport block bits and CRC verdict
     for mode in (0, 1):
         tb = torch.zeros((1, 1, int(case["tbs"])), dtype=torch.uint8, device="cuda"); ok = torch.zeros((1, 1), dtype=torch.int32, device="cuda")
-        ctx.check(ctx.lib.pdsch_decode_batch(ctx.h, dptr(grid), dptr(ce), int(case["N_rb_dl"]), int(case["N_id_cell"]), 1,
+        ctx.check(ctx.lib.pdsch_decode_batch(ctx.h, dptr(grid), dptr(ce), int(case["N_rb_dl"]), int(case["N_id_cell"]), n_tx,
                                              sn.ctypes.data_as(C.c_void_p), 1, int(case["cfi"]), C.byref(al), 1, mode, 8, dptr(tb),
                                              int(case["tbs"]), dptr(ok), stream_ptr()))
         torch.cuda.synchronize()

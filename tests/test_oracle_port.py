@@ -122,3 +122,16 @@ def test_port_against_live_reference(port, refo):
         for rv in (0, 3):
             e = (rng.standard_normal(3 * D + 77) * 2).astype(np.float32)
             assert np.array_equal(port.rate_unmatch_turbo(e, D, rv=rv), phy.rate_unmatch_turbo(e, D, rv=rv))
+
+
+@pytest.mark.parametrize("name", ["loop_2ant_16qam_c21_sf2.npz", "loop_4ant_qpsk_10mhz_c400_sf5.npz", "loop_2ant_64qam_c5_sf7.npz"])
+def test_transmit_diversity_against_reference_fixtures(port, name):
+    """2 / 4 antenna ports: SFBC combining + layer demapping + decode, from the reference's own grid."""
+    c = gold(name)
+    n_tx = int(c["N_ant_tx"])
+    ce_re, ce_im = port.chan_est(c["ref_rx_re"], c["ref_rx_im"], int(c["N_rb_dl"]), int(c["subfr"]), int(c["N_id_cell"]), n_tx)
+    assert np.array_equal(ce_re[:n_tx, :14], c["ref_ce_re"][:n_tx]) and np.array_equal(ce_im[:n_tx, :14], c["ref_ce_im"][:n_tx])
+    rc, bits, soft = port.pdsch_decode_nant(c["ref_rx_re"], c["ref_rx_im"], ce_re, ce_im, int(c["N_rb_dl"]), int(c["N_id_cell"]), n_tx, int(c["subfr"]),
+                                            int(c["cfi"]), int(c["mod"]), c["prb"], int(c["tbs"]), int(c["rnti"]))
+    assert np.array_equal(soft, c["ref_descramb"])
+    assert rc == 0 and np.array_equal(bits, c["ref_tb"]) and np.array_equal(bits, c["tb"])

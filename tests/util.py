@@ -30,25 +30,29 @@ def stream_ptr():
 # Synthetic downlink signal through the REFERENCE's own transmit functions: CRS +
 # PDSCH allocations -> IFFT, followed by a CRS-only subframe (the estimator reads symbols 14-15).
 def ref_loopback(refo, subfr, allocs, N_id_cell=0, cfi=2, N_rb_dl=100, fs=30.72, seed=0, gain=1.0 + 0j, noise=0.0,
-                 frame_start=0, n_extra=1):
+                 frame_start=0, n_extra=1, N_ant=1, ant_gains=None):
     """allocs: list of dict(mod, prb, tbs, rnti).  Returns dict with i/q sample arrays (float32), tb bits, phy handle."""
     rng = np.random.default_rng(seed)
-    phy = refo.RefPhy(fs=fs, N_id_cell=N_id_cell, N_ant=1, N_rb_dl=N_rb_dl)
+    phy = refo.RefPhy(fs=fs, N_id_cell=N_id_cell, N_ant=N_ant, N_rb_dl=N_rb_dl)
+    if ant_gains is None:
+        ant_gains = [1.0, 0.8 * np.exp(0.7j), 0.6 * np.exp(-1.9j), 0.9 * np.exp(2.5j)][:N_ant]
     n_sf = {30.72: 30720, 15.36: 15360, 7.68: 7680, 3.84: 3840, 1.92: 1920}[fs]
     total = frame_start + (subfr + 1 + n_extra) * n_sf + 4096
     i_s = np.zeros(total, np.float32); q_s = np.zeros(total, np.float32)
     tbs_bits = []
     for k in range(1 + n_extra):
         sf = refo.Subframe(); sf.clear(); sf.set_num((subfr + k) % 10)
-        phy.map_crs(sf, N_id_cell, 1)
+        phy.map_crs(sf, N_id_cell, N_ant)
         if k == 0:
             for a in allocs:
                 tb = rng.integers(0, 2, a["tbs"]).astype(np.uint8)
                 tbs_bits.append(tb)
-                phy.pdsch_encode(sf, cfi, N_id_cell, 1, a["mod"], a["prb"], a["tbs"], a["rnti"], tb, rv=a.get("rv", 0))
-        i_sf, q_sf = phy.create_dl_subframe(sf, 0, n_sf)
+                phy.pdsch_encode(sf, cfi, N_id_cell, N_ant, a["mod"], a["prb"], a["tbs"], a["rnti"], tb, rv=a.get("rv", 0))
         o = frame_start + (subfr + k) * n_sf
-        i_s[o:o + n_sf] = i_sf; q_s[o:o + n_sf] = q_sf
+        for ant in range(N_ant):          # flat per-antenna channel, signals add at the receiver
+            i_sf, q_sf = phy.create_dl_subframe(sf, ant, n_sf)
+            za = (i_sf + 1j * q_sf) * ant_gains[ant]
+            i_s[o:o + n_sf] += za.real.astype(np.float32); q_s[o:o + n_sf] += za.imag.astype(np.float32)
     z = (i_s + 1j * q_s) * gain
     if noise > 0:
         z = z + noise * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
