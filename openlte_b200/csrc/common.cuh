@@ -47,6 +47,7 @@ struct lteb200_ctx {
     std::map<int, QppTables> qpp;
     std::map<int, MlmTables> mlm;
     std::map<std::vector<int>, RateUnmatchMap> rum;
+    uint32_t    *crc24a_tab;   // x^j mod g(CRC24A) for j < 6168 (lazily built)
     // statistics
     unsigned long long launches;
 };
@@ -70,5 +71,6 @@ struct Bump {
 };
 
 int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out);
+int lteb200_get_crc24a_tab(lteb200_ctx *ctx, const uint32_t **out);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -33,6 +33,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->arena = nullptr;
     c->arena_bytes = 0;
     c->launches = 0;
+    c->crc24a_tab = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
     // otherwise every host-pointer call would re-acquire gigabytes from the driver.
@@ -51,6 +52,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
+    if (c->crc24a_tab) cudaFree(c->crc24a_tab);
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
     for (auto &kv : c->rum) cudaFree(kv.second.first_k);
@@ -100,5 +102,22 @@ int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out)
     LTE_CUDA_OK(ctx, cudaMemcpy(t.inv_last, inv.data(), K * sizeof(int16_t), cudaMemcpyHostToDevice));
     ctx->qpp[K] = t;
     *out = t;
+    return LTEB200_OK;
+}
+
+int lteb200_get_crc24a_tab(lteb200_ctx *ctx, const uint32_t **out)
+{
+    if (!ctx->crc24a_tab) {
+        std::vector<uint32_t> t(6168);
+        uint32_t v = 1;
+        for (int j = 0; j < 6168; j++) {        // x^j mod g, g = 0x1864CFB (calc_crc's long division, liblte_phy.cc:9713-9743)
+            t[j] = v;
+            v <<= 1;
+            if (v & 0x1000000u) v ^= 0x1864CFBu;
+        }
+        LTE_CUDA_OK(ctx, cudaMalloc(&ctx->crc24a_tab, sizeof(uint32_t) * t.size()));
+        LTE_CUDA_OK(ctx, cudaMemcpy(ctx->crc24a_tab, t.data(), sizeof(uint32_t) * t.size(), cudaMemcpyHostToDevice));
+    }
+    *out = ctx->crc24a_tab;
     return LTEB200_OK;
 }

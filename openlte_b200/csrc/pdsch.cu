@@ -11,6 +11,7 @@
 // an index list per class; the kernel is then a fused gather -> ZF -> demap -> descramble, one thread per resource
 // element, reading grid and channel estimate once (8 B + 8 B) and writing Q_m floats: HBM-bound.
 #include "internal.h"
+#include "pdsch_dev.cuh"
 #include <math.h>
 
 namespace {
@@ -21,45 +22,10 @@ struct DemodParams {
     int soft_stride;  // floats per subframe in the output
 };
 
-__device__ __forceinline__ float soft_dist(float re, float im, float ere, float eim)
-{
-    // get_soft_decision(rx, exp, max_dist = 1): 1 - min(dist, 1 - 1/120)
-    const float dr = __fsub_rn(re, ere), di = __fsub_rn(im, eim);
-    float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di)));
-    const float lim = __fsub_rn(1.0f, __fdiv_rn(1.0f, 120.0f));
-    if (dist >= lim) dist = lim;
-    return __fsub_rn(1.0f, dist);
-}
-
 __device__ __forceinline__ void demap_store(float xr, float xi, int mod, int Qm, const uint8_t *__restrict__ c, float *__restrict__ o)
 {
     int b[6];
-    const float r2 = 0.70710678118654752440f;
-    if (mod == LTEB200_MOD_QPSK) {
-        const float ang = atan2f(xi, xr);
-        const double a = (double)ang, hp = 1.57079632679489661923, pi = 3.14159265358979323846;
-        int s0, s1;
-        if (a >= 0 && a < hp) { s0 = 1; s1 = 1; }
-        else if (a >= -hp && a < 0) { s0 = 1; s1 = -1; }
-        else if (a >= hp && a < pi) { s0 = -1; s1 = 1; }
-        else { s0 = -1; s1 = -1; }
-        const int m = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, s0 > 0 ? r2 : -r2, s1 > 0 ? r2 : -r2)));
-        b[0] = s0 * m; b[1] = s1 * m;
-    } else if (mod == LTEB200_MOD_16QAM) {
-        const float t = 0.63245553203367586640f;  // 2/sqrt(10)
-        b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
-        b[2] = fabsf(xr) < t ? 127 : -127; b[3] = fabsf(xi) < t ? 127 : -127;
-    } else if (mod == LTEB200_MOD_64QAM) {
-        const float t2 = 0.30860669992418382490f, t4 = 0.61721339984836764980f, t6 = 0.92582009977255147470f;  // {2,4,6}/sqrt(42)
-        const float ar = fabsf(xr), ai = fabsf(xi);
-        b[0] = xr > 0 ? 127 : -127; b[1] = xi > 0 ? 127 : -127;
-        if (ar < t4) { b[2] = 127; b[4] = ar > t2 ? 127 : -127; } else { b[2] = -127; b[4] = ar < t6 ? 127 : -127; }
-        if (ai < t4) { b[3] = 127; b[5] = ai > t2 ? 127 : -127; } else { b[3] = -127; b[5] = ai < t6 ? 127 : -127; }
-    } else {  // BPSK
-        const double a = (double)atan2f(xi, xr), pi = 3.14159265358979323846;
-        if (a > -pi / 4 && a < 3 * pi / 4) b[0] = __float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, r2, r2)));
-        else b[0] = -__float2int_rz(__fmul_rn(127.0f, soft_dist(xr, xi, -r2, -r2)));
-    }
+    demap_bits(xr, xi, mod, b);
     for (int t = 0; t < Qm; t++) o[t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)c[t]));  // soft * (1 - 2c), :3835
 }
 
@@ -220,6 +186,7 @@ static int seg_params(int tbs, int *K, int *F)
 }
 
 void prs_c_host(uint32_t c_init, int len, uint8_t *c);
+int turbo_mlm_fused_batch(lteb200_ctx *ctx, int K, int n_iter, const FusedParams &fp, cudaStream_t stream);
 int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv, RateUnmatchMap *out);
 int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, const int *d_E, int D, const RateUnmatchMap &m, int n_cb,
                             float *d_out, cudaStream_t stream);
@@ -337,6 +304,37 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[a], &T[a]);
         if (rc) return rc;
         if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+    }
+    // ---- fused path: one kernel per group of allocations with equal K does demod + unmatch + decode + CRC per transport block
+    if (turbo_mode == LTEB200_TURBO_MAXLOGMAP && N_ant == 1 && !getenv("LTEB200_NO_FUSE")) {
+        int *d_sn = nullptr;
+        rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, stream);
+        if (rc) return rc;
+        const uint32_t *crc_tab = nullptr;
+        rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
+        for (int a = 0; a < n_alloc && rc == LTEB200_OK;) {
+            FusedParams fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.crc_tab = crc_tab;
+            fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
+            int e = a;
+            while (e < n_alloc && e - a < 8 && T[e].K == T[a].K) {
+                RateUnmatchMap m;
+                rc = rate_unmatch_get_map(ctx, T[e].K + 4, 0, 1, allocs[e].tx_mode, 250368, 8, 0, allocs[e].rv_idx, &m);
+                if (rc) break;
+                FusedAlloc &A = fp.al[e - a];
+                A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.first_k = m.first_k; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
+                for (int c = 0; c < 3; c++) A.M[c] = T[e].M[c];
+                A.Qm = T[e].Qm; A.mod = allocs[e].mod_type; A.period = m.n_nonnull; A.F = T[e].F; A.tbs = allocs[e].tbs; A.a_idx = e;
+                e++;
+            }
+            if (rc) break;
+            fp.n_al = e - a;
+            rc = turbo_mlm_fused_batch(ctx, T[a].K, n_iter, fp, stream);
+            a = e;
+        }
+        cudaFreeAsync(d_sn, stream);
+        return rc;
     }
     // per-call device parameter arrays: subframe numbers and per-(alloc, subframe) E
     std::vector<int> hpar((size_t)n_sf * (1 + n_alloc));

@@ -15,6 +15,7 @@
 // arrays use a window-transposed layout pos(k) = (k mod 32)*nw + k/32 so that at every step the threads of a
 // warp touch consecutive addresses (conflict free).  No tensor cores (no contraction on this path).
 #include "common.cuh"
+#include "pdsch_dev.cuh"
 
 #ifndef MLM_WIN
 #define MLM_WIN 16   // window length (steps per thread); oracle/port/turbo_mlm.cc must use the same value
@@ -168,10 +169,16 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
 
 // piT  [WIN*NT] : pos(pi(k)) stored at pos(k), pos(k) = (k mod WIN)*NT + k/WIN, NT = 6144/WIN    (global, per K)
 // csr_start [NP+1], csr_pos [K] : for POSITION p = pos(j), the positions pos(i) of all i with pi(i) == j   (global, per K)
-template <int WIN>
+// FUSED == false: input = rate-unmatched LLRs llr[n_cb][3(K+4)], output = decoded bits out[n_cb][K].
+// FUSED == true : the whole PDSCH receive of one transport block in one kernel -- RE extraction, ZF, demapping and
+//                 descrambling into shared memory (aliasing the forward-metric store, which is idle until the first pass),
+//                 rate unmatching through the gather map straight into each thread's window, decoding, then CRC24A and
+//                 transport-block extraction from the decisions.  Block index = local_alloc * n_sf + subframe.
+template <int WIN, bool FUSED>
 __global__ void __launch_bounds__(WIN == 32 ? 192 : 384)
 turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_t *__restrict__ piT,
-                 const uint16_t *__restrict__ csr_start, const uint16_t *__restrict__ csr_pos, uint8_t *__restrict__ out)
+                 const uint16_t *__restrict__ csr_start, const uint16_t *__restrict__ csr_pos, uint8_t *__restrict__ out,
+                 const __grid_constant__ FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = 6144 / WIN;   // row stride of the window-transposed arrays (compile-time: largest block size)
@@ -197,7 +204,50 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     float m = 0.f;
     const bool own = tid < nw;
     const int nown = own ? min(WIN, K - WIN * tid) : 0;
-    if (nown == WIN) {
+    float tail_v = 0.f;
+    if (FUSED) {
+        const int a_loc = cb / fp.n_sf, sf = cb - a_loc * fp.n_sf;
+        const FusedAlloc &A = fp.al[a_loc];
+        const int sn = fp.subfr_num[sf];
+        const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
+        const int M = A.M[cls], E = M * A.Qm;
+        float *soft = reinterpret_cast<float *>(st);                       // <= 20,700 floats, the metric store is idle now
+        const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * 14 * fp.nsc;
+        const int *ix = A.re_idx + cls * A.idx_stride;
+        const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
+        for (int r = tid; r < M; r += nt) {
+            const int idx = ix[r];
+            float xr, xi;
+            zf_1port(gr[idx], ch[idx], xr, xi);
+            int b[6];
+            demap_bits(xr, xi, A.mod, b);
+            for (int t = 0; t < A.Qm; t++) soft[r * A.Qm + t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)cs[r * A.Qm + t]));
+        }
+        __syncthreads();
+        // rate unmatching (liblte_phy.cc:11403-11415): first visit assigns, repeats are added in visiting order
+        auto unmatch = [&](int fk) -> float {
+            float w = LTEB200_RX_NULL_BIT;
+            if (fk >= 0)
+                for (int k = fk; k < E; k += A.period) {
+                    const float x = soft[k];
+                    if (w == LTEB200_RX_NULL_BIT) w = x; else if (x != LTEB200_RX_NULL_BIT) w = __fadd_rn(w, x);
+                }
+            return w;
+        };
+        if (nown == WIN) {
+            const int4 *fk4 = reinterpret_cast<const int4 *>(A.first_k + 3 * WIN * tid);
+#pragma unroll
+            for (int j = 0; j < 3 * WIN / 4; j++) {
+                const int4 f = fk4[j];
+                v[4 * j] = unmatch(f.x); v[4 * j + 1] = unmatch(f.y); v[4 * j + 2] = unmatch(f.z); v[4 * j + 3] = unmatch(f.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3 * WIN; j++) v[j] = (j < 3 * nown) ? unmatch(A.first_k[3 * WIN * tid + j]) : 0.f;
+        }
+        if (tid < 12) tail_v = unmatch(A.first_k[3 * K + tid]);
+        __syncthreads();                                                   // soft[] is dead from here on
+    } else if (nown == WIN) {
         const float4 *src = reinterpret_cast<const float4 *>(d + 3 * WIN * tid);
 #pragma unroll
         for (int j = 0; j < 3 * WIN / 4; j++) {
@@ -214,9 +264,9 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         m = fmaxf(m, fabsf(v[j]));
     }
     if (tid < 12) {                              // the 12 tail values take part in the maximum
-        float t = d[3 * K + tid];
-        if (t == LTEB200_RX_NULL_BIT) t = 0.f;
-        m = fmaxf(m, fabsf(t));
+        if (!FUSED) tail_v = d[3 * K + tid];
+        if (tail_v == LTEB200_RX_NULL_BIT) tail_v = 0.f;
+        m = fmaxf(m, fabsf(tail_v));
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) s_red[tid >> 5] = m;
@@ -238,11 +288,7 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
             Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2; Lsa1[p] = (int16_t)q0;
         }
     }
-    if (tid < 12) {
-        float tv = d[3 * K + tid];
-        if (tv == LTEB200_RX_NULL_BIT) tv = 0.f;
-        s_tail[tid] = qf(tv, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
-    }
+    if (tid < 12) s_tail[tid] = qf(tail_v, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
     for (int i = tid; i < NT * 4; i += nt) bA1[i] = make_uint4(0, 0, 0, 0);  // bA1,bB1,bA2,bB2 are contiguous
     for (int p = tid; p < NP; p += nt) s_piT[p] = piT[p];
     for (int j = tid; j <= NP; j += nt) s_cs[j] = csr_start[j];
@@ -278,15 +324,56 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         }
         __syncthreads();
     }
-    for (int j = tid; j < K; j += nt) {
-        const int p = (j % WIN) * NT + (j / WIN);
-        out[(size_t)cb * K + j] = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
+    if (!FUSED) {
+        for (int j = tid; j < K; j += nt) {
+            const int p = (j % WIN) * NT + (j / WIN);
+            out[(size_t)cb * K + j] = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
+        }
+    } else {
+        // dlsch_channel_decode's tail (liblte_phy.cc:12841-12869): drop the F filler bits, CRC24A over [a | p], emit a.
+        // The remainder of the tbs+24 bit message is the XOR of x^(distance from the end) mod g over its set bits.
+        const int a_loc = cb / fp.n_sf, sf = cb - a_loc * fp.n_sf;
+        const FusedAlloc &A = fp.al[a_loc];
+        const int n = A.tbs + 24;
+        uint8_t *o = fp.tb_out + ((size_t)sf * fp.n_alloc_total + A.a_idx) * fp.tb_stride;
+        uint32_t rem = 0;
+        for (int j = tid; j < K; j += nt) {
+            const int p = (j % WIN) * NT + (j / WIN);
+            const int bit = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
+            const int idx = j - A.F;
+            if (idx >= 0) {
+                if (idx < A.tbs) o[idx] = (uint8_t)bit;
+                if (bit) rem ^= fp.crc_tab[n - 1 - idx];
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, off);
+        __syncthreads();
+        if ((tid & 31) == 0) s_tail[tid >> 5] = (int)rem;                  // <= 12 warps
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t r = 0;
+            for (int wv = 0; wv < (nt >> 5); wv++) r ^= (uint32_t)s_tail[wv];
+            fp.crc_ok[(size_t)sf * fp.n_alloc_total + A.a_idx] = (r & 0xffffffu) == 0 ? 1 : 0;
+        }
     }
 }
 
 }  // namespace
 
+static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream);
+
 int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, cudaStream_t stream)
+{
+    return turbo_mlm_launch(ctx, d_llr, K, n_cb, n_iter, d_bits, nullptr, stream);
+}
+
+// Fused PDSCH receive: n_cb = fp.n_al * fp.n_sf transport blocks of the same K.
+int turbo_mlm_fused_batch(lteb200_ctx *ctx, int K, int n_iter, const FusedParams &fp, cudaStream_t stream)
+{
+    return turbo_mlm_launch(ctx, nullptr, K, fp.n_al * fp.n_sf, n_iter, nullptr, &fp, stream);
+}
+
+static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream)
 {
     if (K < 40 || (K & 7) || K > 6144) { lteb200_set_error(ctx, "turbo: illegal K=%d", K); return LTEB200_ERR_ARGS; }
     if (n_iter < 1) n_iter = 1;
@@ -320,9 +407,16 @@ int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
         } else mt = it->second;
     }
     const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)4 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
-    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = ((nw + 31) / 32) * 32;
-    turbo_mlm_kernel<WIN><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits);
+    if (fused) {
+        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        turbo_mlm_kernel<WIN, true><<<n_cb, threads, smem, stream>>>(nullptr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, nullptr, *fused);
+    } else {
+        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FusedParams none;
+        memset(&none, 0, sizeof(none));
+        turbo_mlm_kernel<WIN, false><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits, none);
+    }
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;

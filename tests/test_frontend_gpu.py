@@ -157,3 +157,39 @@ def test_host_twins(ctx, port):
                                       int(case["cfi"]), int(case["N_id_cell"]), 1, 0, 0, p(out2), C.byref(n2))
     assert rc == -3 and n2.value == 77 and (out2 == 9).all()
     assert ctx.lib.pdsch_channel_decode(ctx.h, None, p(rx_im), p(ce_re), p(ce_im), 100, 1, C.byref(al), 2, 0, 1, 0, 0, p(out), C.byref(n)) == -1
+
+
+def test_fused_receive_equals_staged_pipeline(ctx):
+    """The single-kernel PDSCH receive (demod + rate unmatch + max-log-MAP + CRC fused per transport block) must give exactly
+    what the staged kernels give, on a batch with subframes 0 and 5 in it (different RE counts per subframe class)."""
+    import torch
+    from openlte_b200 import synth
+    cell, n_sf = 17, 12
+    allocs = [dict(mod=3, prb=list(range(25 * a, 25 * a + 25)), tbs=6120, rnti=0x100 + a) for a in range(4)]
+    allocs.append(dict(mod=1, prb=list(range(45, 55)), tbs=712, rnti=0x77))       # overlaps the centre band; different K
+    allocs[1]["prb"] = list(range(25, 45)); allocs[1]["tbs"] = 4968; allocs[1]["mod"] = 3
+    allocs[2]["prb"] = list(range(55, 75)); allocs[2]["tbs"] = 4968
+    tx = synth.make_subframes(n_sf, allocs, N_id_cell=cell, seed=11, noise=0.6, first_subfr=8)
+    tail = synth.crs_only_tail(100, cell, int((tx["subfr_nums"][-1] + 1) % 10), 4)
+    stream = np.concatenate([tx["samples"].reshape(-1), tail])
+    iq = np.stack([stream.real, stream.imag], -1).astype(np.float32)
+    d_iq = torch.from_numpy(iq).cuda()
+    start = (np.arange(n_sf) * 30720).astype(np.int64); sn = tx["subfr_nums"].astype(np.int32)
+    c_allocs = (Alloc * len(allocs))(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    res = {}
+    for fuse in (True, False):
+        if fuse:
+            os.environ.pop("LTEB200_NO_FUSE", None)
+        else:
+            os.environ["LTEB200_NO_FUSE"] = "1"
+        tb = torch.full((n_sf, len(allocs), 6120), 9, dtype=torch.uint8, device="cuda")
+        ok = torch.zeros((n_sf, len(allocs)), dtype=torch.int32, device="cuda")
+        ctx.check(ctx.lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, start.ctypes.data_as(C.c_void_p),
+                                           sn.ctypes.data_as(C.c_void_p), n_sf, 2, c_allocs, len(allocs), 1, 8, dptr(tb), 6120, dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        res[fuse] = (tb.cpu().numpy(), ok.cpu().numpy())
+    os.environ.pop("LTEB200_NO_FUSE", None)
+    assert np.array_equal(res[True][1], res[False][1]) and res[True][1].all()
+    for a, al in enumerate(allocs):
+        assert np.array_equal(res[True][0][:, a, :al["tbs"]], res[False][0][:, a, :al["tbs"]])
+        assert np.array_equal(res[True][0][:, a, :al["tbs"]], tx["tb"][a])
