@@ -195,30 +195,80 @@ extern "C" int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int 
     return rc;
 }
 
+// Host-pointer entry point.  The batch is cut into chunks of subframes that flow through a three-stage pipeline on
+// three streams -- H2D copy of a chunk's samples, the receive kernels, D2H copy of its transport blocks -- so that PCIe
+// traffic in both directions overlaps the kernels (pinned host buffers make the copies truly asynchronous; pageable
+// ones still work, staged by the driver).  start_idx must be non-decreasing.
 extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl, int N_id_cell,
                                        int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf, int N_pdcch_symbs,
                                        const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter, uint8_t *h_tb_bits, int tb_stride,
                                        int32_t *h_crc_ok)
 {
-    if (!ctx || !h_iq || !h_tb_bits || !h_crc_ok || n_sf < 1 || n_alloc < 1 || n_samps < 1) return LTEB200_ERR_ARGS;
+    if (!ctx || !h_iq || !h_start_idx || !h_subfr_num || !h_tb_bits || !h_crc_ok || n_sf < 1 || n_alloc < 1 || n_samps < 1 || fs_idx < 0 || fs_idx > 4)
+        return LTEB200_ERR_ARGS;
+    for (int i = 1; i < n_sf; i++)
+        if (h_start_idx[i] < h_start_idx[i - 1]) { lteb200_set_error(ctx, "dl_receive_host: start_idx must be non-decreasing"); return LTEB200_ERR_ARGS; }
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     const size_t samp_bytes = iq_fmt == LTEB200_IQ_I8 ? 2 : 8;
+    if (!ctx->s_h2d) {
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    int chunk = n_sf / 8;
+    if (const char *e = getenv("LTEB200_E2E_CHUNK")) chunk = atoi(e);
+    if (chunk < 64) chunk = 64;
+    if (chunk > n_sf) chunk = n_sf;
+    const int n_chunks = (n_sf + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev_h(n_chunks), ev_c(n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+        LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_h[c], cudaEventDisableTiming));
+        LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_c[c], cudaEventDisableTiming));
+    }
+    cudaEvent_t ev_alloc;
+    LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
     void *d_iq = nullptr;
     uint8_t *d_tb = nullptr;
     int32_t *d_ok = nullptr;
-    cudaStream_t stream = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_iq, samp_bytes * n_samps, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)n_sf * n_alloc * tb_stride, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_iq, h_iq, samp_bytes * n_samps, cudaMemcpyHostToDevice, stream));
-    int rc = lteb200_dl_receive_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx, h_subfr_num, n_sf, N_pdcch_symbs,
-                                      allocs, n_alloc, turbo_mode, n_iter, d_tb, tb_stride, d_ok, stream);
-    if (rc == LTEB200_OK) {
-        cudaMemcpyAsync(h_tb_bits, d_tb, (size_t)n_sf * n_alloc * tb_stride, cudaMemcpyDeviceToHost, stream);
-        cudaMemcpyAsync(h_crc_ok, d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, cudaMemcpyDeviceToHost, stream);
+    const size_t tb_row = (size_t)n_alloc * tb_stride;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_iq, samp_bytes * n_samps, ctx->s_comp));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)n_sf * tb_row, ctx->s_comp));
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, ctx->s_comp));
+    LTE_CUDA_OK(ctx, cudaEventRecord(ev_alloc, ctx->s_comp));
+    LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_alloc, 0));
+    LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_alloc, 0));
+    // stage 1: sample slices, back to back.  Chunk c owns [start(c), start(c+1)); the last one runs to the end of the buffer.
+    for (int c = 0; c < n_chunks; c++) {
+        long long lo = c == 0 ? 0 : h_start_idx[(size_t)c * chunk];
+        long long hi = c + 1 < n_chunks ? h_start_idx[(size_t)(c + 1) * chunk] : n_samps;
+        if (lo < 0) lo = 0;
+        if (hi > n_samps) hi = n_samps;
+        if (hi > lo)
+            LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * lo, (const char *)h_iq + samp_bytes * lo, samp_bytes * (size_t)(hi - lo),
+                                            cudaMemcpyHostToDevice, ctx->s_h2d));
+        LTE_CUDA_OK(ctx, cudaEventRecord(ev_h[c], ctx->s_h2d));
     }
-    cudaFreeAsync(d_iq, stream); cudaFreeAsync(d_tb, stream); cudaFreeAsync(d_ok, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (rc == LTEB200_OK && e != cudaSuccess) { lteb200_set_error(ctx, "dl_receive_host: %s", cudaGetErrorString(e)); rc = LTEB200_ERR_CUDA; }
+    int rc = LTEB200_OK;
+    for (int c = 0; c < n_chunks && rc == LTEB200_OK; c++) {
+        const int b0 = c * chunk, nb = (n_sf - b0) < chunk ? (n_sf - b0) : chunk;
+        // a chunk's last subframe looks two symbols into the next chunk's samples: wait for that copy too
+        LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_comp, ev_h[c + 1 < n_chunks ? c + 1 : c], 0));
+        rc = lteb200_dl_receive_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx + b0, h_subfr_num + b0, nb, N_pdcch_symbs,
+                                      allocs, n_alloc, turbo_mode, n_iter, d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
+        if (rc) break;
+        LTE_CUDA_OK(ctx, cudaEventRecord(ev_c[c], ctx->s_comp));
+        LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_c[c], 0));
+        LTE_CUDA_OK(ctx, cudaMemcpyAsync(h_tb_bits + (size_t)b0 * tb_row, d_tb + (size_t)b0 * tb_row, (size_t)nb * tb_row, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        LTE_CUDA_OK(ctx, cudaMemcpyAsync(h_crc_ok + (size_t)b0 * n_alloc, d_ok + (size_t)b0 * n_alloc, sizeof(int32_t) * (size_t)nb * n_alloc,
+                                        cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    cudaFreeAsync(d_iq, ctx->s_comp); cudaFreeAsync(d_tb, ctx->s_comp); cudaFreeAsync(d_ok, ctx->s_comp);
+    for (int c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_h[c]); cudaEventDestroy(ev_c[c]); }
+    cudaEventDestroy(ev_alloc);
+    if (rc == LTEB200_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+        lteb200_set_error(ctx, "dl_receive_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        rc = LTEB200_ERR_CUDA;
+    }
     return rc;
 }

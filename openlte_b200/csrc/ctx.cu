@@ -34,6 +34,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->arena_bytes = 0;
     c->launches = 0;
     c->crc24a_tab = nullptr;
+    c->s_h2d = c->s_comp = c->s_d2h = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
     // otherwise every host-pointer call would re-acquire gigabytes from the driver.
@@ -53,6 +54,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
     if (c->crc24a_tab) cudaFree(c->crc24a_tab);
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); }
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
     for (auto &kv : c->rum) cudaFree(kv.second.first_k);

@@ -193,3 +193,30 @@ def test_fused_receive_equals_staged_pipeline(ctx):
     for a, al in enumerate(allocs):
         assert np.array_equal(res[True][0][:, a, :al["tbs"]], res[False][0][:, a, :al["tbs"]])
         assert np.array_equal(res[True][0][:, a, :al["tbs"]], tx["tb"][a])
+
+
+def test_host_pointer_pipeline_equals_device_path(ctx):
+    """lteb200_dl_receive_host (chunked H2D / kernels / D2H pipeline, int8 capture-format samples) against the device-resident call."""
+    import torch
+    from openlte_b200 import synth
+    cell, n_sf = 33, 150
+    allocs = [dict(mod=3, prb=list(range(25 * a, 25 * a + 25)), tbs=6120, rnti=0x200 + a) for a in range(2)]
+    tx = synth.make_subframes(10, allocs, N_id_cell=cell, seed=21, first_subfr=3)
+    seg = tx["samples"].reshape(-1)
+    stream = np.concatenate([np.tile(seg, n_sf // 10), synth.crs_only_tail(100, cell, 3, 4)[:8192]])
+    sc = 100.0 / np.abs(np.concatenate([stream.real, stream.imag])).max()
+    iq = np.stack([np.rint(stream.real * sc), np.rint(stream.imag * sc)], -1).astype(np.int8)
+    start = (np.arange(n_sf) * 30720).astype(np.int64); sn = ((3 + np.arange(n_sf)) % 10).astype(np.int32)
+    c_allocs = (Alloc * 2)(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    h_tb = np.full((n_sf, 2, 6120), 7, np.uint8); h_ok = np.zeros((n_sf, 2), np.int32)
+    pv = lambda a: a.ctypes.data_as(C.c_void_p)
+    os.environ["LTEB200_E2E_CHUNK"] = "64"
+    try:
+        for mode in (1, 0):
+            ctx.check(ctx.lib.dl_receive_host(ctx.h, pv(iq), 1, iq.shape[0], 4, 100, cell, 1, pv(start), pv(sn), n_sf, 2, c_allocs, 2, mode, 8, pv(h_tb), 6120, pv(h_ok)))
+            assert h_ok.all()
+            for a in range(2):
+                assert np.array_equal(h_tb[:, a], np.tile(tx["tb"][a], (n_sf // 10, 1)))
+            h_tb[:] = 7; h_ok[:] = 0
+    finally:
+        os.environ.pop("LTEB200_E2E_CHUNK", None)
