@@ -215,13 +215,27 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * 14 * fp.nsc;
         const int *ix = A.re_idx + cls * A.idx_stride;
         const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
-        for (int r = tid; r < M; r += nt) {
-            const int idx = ix[r];
-            float xr, xi;
-            zf_1port(gr[idx], ch[idx], xr, xi);
-            int b[6];
-            demap_bits(xr, xi, A.mod, b);
-            for (int t = 0; t < A.Qm; t++) soft[r * A.Qm + t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)cs[r * A.Qm + t]));
+        // every thread handles up to RE_IT resource elements; indices, grid and estimate values are all fetched before the
+        // arithmetic starts, so the global-memory latency is paid once, not per element
+        constexpr int RE_IT = 4;
+        for (int r0 = tid; r0 < M; r0 += RE_IT * nt) {
+            int idx[RE_IT];
+            float2 yv[RE_IT], hv[RE_IT];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) idx[u] = (r0 + u * nt < M) ? ix[r0 + u * nt] : ix[r0];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) { yv[u] = gr[idx[u]]; hv[u] = ch[idx[u]]; }
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) {
+                const int r = r0 + u * nt;
+                if (r < M) {
+                    float xr, xi;
+                    zf_1port(yv[u], hv[u], xr, xi);
+                    int b[6];
+                    demap_bits(xr, xi, A.mod, b);
+                    for (int t = 0; t < A.Qm; t++) soft[r * A.Qm + t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)cs[r * A.Qm + t]));
+                }
+            }
         }
         __syncthreads();
         // rate unmatching (liblte_phy.cc:11403-11415): first visit assigns, repeats are added in visiting order
@@ -337,13 +351,32 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         const int n = A.tbs + 24;
         uint8_t *o = fp.tb_out + ((size_t)sf * fp.n_alloc_total + A.a_idx) * fp.tb_stride;
         uint32_t rem = 0;
-        for (int j = tid; j < K; j += nt) {
-            const int p = (j % WIN) * NT + (j / WIN);
-            const int bit = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
-            const int idx = j - A.F;
-            if (idx >= 0) {
-                if (idx < A.tbs) o[idx] = (uint8_t)bit;
-                if (bit) rem ^= fp.crc_tab[n - 1 - idx];
+        if (tid < nw) {
+            // thread w decides its own 16 steps (conflict-free column reads), j = 16w + i
+            const int nown_e = min(WIN, K - WIN * tid);
+            unsigned long long packed[2] = {0ull, 0ull};                  // one byte per bit, 16 bytes
+#pragma unroll
+            for (int i = 0; i < WIN; i++) {
+                const int p = i * NT + tid;
+                const int bit = (i < nown_e && ((int)Lsa1[p] + (int)Le1[p] < 0)) ? 1 : 0;
+                packed[i >> 3] |= (unsigned long long)bit << (8 * (i & 7));
+            }
+            const int idx0 = WIN * tid - A.F;                              // index of this thread's first bit inside [a | p]
+            const bool fast = A.F == 0 && nown_e == WIN && idx0 + WIN <= A.tbs && (fp.tb_stride & 7) == 0 && ((size_t)o & 7) == 0;
+            if (fast) {
+                reinterpret_cast<unsigned long long *>(o + idx0)[0] = packed[0];
+                reinterpret_cast<unsigned long long *>(o + idx0)[1] = packed[1];
+            } else {
+#pragma unroll
+                for (int i = 0; i < WIN; i++) {
+                    const int idx = idx0 + i;
+                    if (i < nown_e && idx >= 0 && idx < A.tbs) o[idx] = (uint8_t)((packed[i >> 3] >> (8 * (i & 7))) & 1);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < WIN; i++) {
+                const int idx = idx0 + i;
+                if (i < nown_e && idx >= 0 && ((packed[i >> 3] >> (8 * (i & 7))) & 1)) rem ^= fp.crc_tab[n - 1 - idx];
             }
         }
         for (int off = 16; off > 0; off >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, off);
