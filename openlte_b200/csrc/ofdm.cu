@@ -92,6 +92,153 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident mixed-radix variant (the batched subframe path).  N = 16*16*8 (2048), 16*16*4, 16*8*4, 16*16, 16*8:
+// N/16 threads per symbol, every thread carries 16 complex values through each Stockham pass as one radix-16 butterfly
+// (or 16/R radix-R butterflies) held entirely in registers, so a 2048-point transform crosses shared memory twice
+// instead of six times and needs three barriers.  The first pass reads the samples straight from global memory
+// (coalesced: thread b reads x[b + (N/16) k]), the last one writes the used bins straight to the grid.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mulmj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
+
+template <int R> struct Dft;
+template <> struct Dft<2> {
+    __device__ __forceinline__ static void run(float2 *x) { const float2 a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
+};
+template <> struct Dft<4> {
+    __device__ __forceinline__ static void run(float2 *x)
+    {
+        const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]), t2 = cadd(x[1], x[3]), t3 = mulmj(csub(x[1], x[3]));
+        x[0] = cadd(t0, t2); x[1] = cadd(t1, t3); x[2] = csub(t0, t2); x[3] = csub(t1, t3);
+    }
+};
+template <> struct Dft<8> {
+    __device__ __forceinline__ static void run(float2 *x)
+    {
+        float2 e[4] = {x[0], x[2], x[4], x[6]}, o[4] = {x[1], x[3], x[5], x[7]};
+        Dft<4>::run(e); Dft<4>::run(o);
+        const float r = 0.70710678118654752440f;
+        const float2 w1 = make_float2(r, -r), w3 = make_float2(-r, -r);
+        const float2 o1 = cmul(o[1], w1), o2 = mulmj(o[2]), o3 = cmul(o[3], w3);
+        x[0] = cadd(e[0], o[0]); x[4] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o1);   x[5] = csub(e[1], o1);
+        x[2] = cadd(e[2], o2);   x[6] = csub(e[2], o2);
+        x[3] = cadd(e[3], o3);   x[7] = csub(e[3], o3);
+    }
+};
+template <> struct Dft<16> {
+    __device__ __forceinline__ static void run(float2 *x)
+    {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+        Dft<8>::run(e); Dft<8>::run(o);
+        // W16^k = exp(-j pi k / 8)
+        const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, r = 0.70710678118654752440f;
+        const float2 w[8] = {make_float2(1.f, 0.f), make_float2(c1, -s1), make_float2(r, -r), make_float2(s1, -c1),
+                             make_float2(0.f, -1.f), make_float2(-s1, -c1), make_float2(-r, -r), make_float2(-c1, -s1)};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float2 t = (k == 0) ? o[0] : ((k == 4) ? mulmj(o[4]) : cmul(o[k], w[k]));
+            x[k] = cadd(e[k], t); x[k + 8] = csub(e[k], t);
+        }
+    }
+};
+
+// One Stockham pass of radix R over a transform of current length n and stride s (n * s == N); thread `tid` handles
+// butterflies tid, tid + NTHR, ...  SRC_GLOBAL: inputs come from the sample stream (first pass); DST_GRID: outputs go
+// to the resource grid through the bin -> subcarrier map (last pass, where p == 0 and no twiddle applies).
+template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID>
+__device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long long w0, long long n_samps, const float2 *__restrict__ src,
+                                              float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid)
+{
+    constexpr int NTHR = N / 16, s = N / n, n1 = n / R;
+#pragma unroll
+    for (int rep = 0; rep < 16 / R; rep++) {
+        const int b = tid + rep * NTHR;            // butterfly index in [0, N/R)
+        const int p = b / s, q = b - p * s;
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int i = q + s * (p + n1 * k);
+            if (SRC_GLOBAL) {
+                const long long sidx = w0 + i;
+                x[k] = (sidx >= 0 && sidx < n_samps) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
+            } else x[k] = src[i];
+        }
+        Dft<R>::run(x);
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (DST_GRID) {
+                const int bin = q + s * k;         // p == 0 in the last pass
+                if (bin >= 1 && bin <= h) out[h + bin - 1] = x[k];
+                else if (bin >= N - h) out[bin - (N - h)] = x[k];
+            } else {
+                const float2 v = (k == 0 || p == 0) ? x[k] : cmul(x[k], __ldg(&tw[p * k * s]));
+                dst[q + s * (R * p + k)] = v;
+            }
+        }
+    }
+}
+
+template <int N, typename T>
+__global__ void __launch_bounds__(N / 16 < 32 ? 32 : N / 16)
+ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
+                      const float2 *__restrict__ tw, float2 *__restrict__ grid)
+{
+    __shared__ float2 bufA[N], bufB[N];
+    const int tid = threadIdx.x;
+    const int sf = blockIdx.x >> 4, sym = blockIdx.x & 15;
+    const int slot = sym / 7, l = sym % 7;
+    const long long w0 = start_idx[sf] + (long long)slot * P.slot + (long long)(P.N + P.cpe) * l + (l > 0 ? P.cp0 - P.cpe : 0) +
+                         (l == 0 ? P.cp0 : P.cpe) - 1;
+    float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
+    const bool act = tid < N / 16;
+    if constexpr (N == 2048) {          // 16 x 16 x 8
+        if (act) stockham_pass<N, 16, 2048, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 16, 128, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
+    } else if constexpr (N == 1024) {   // 16 x 16 x 4
+        if (act) stockham_pass<N, 16, 1024, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 16, 64, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
+    } else if constexpr (N == 512) {    // 16 x 8 x 4
+        if (act) stockham_pass<N, 16, 512, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 8, 32, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
+    } else if constexpr (N == 256) {    // 16 x 16
+        if (act) stockham_pass<N, 16, 256, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 16, 16, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
+    } else {                  // 128 = 16 x 8
+        if (act) stockham_pass<N, 16, 128, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        __syncthreads();
+        if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
+    }
+}
+
+template <typename T>
+static void launch_r16(const T *iq, long long n_samps, const long long *d_start, const OfdmParams &P, const float2 *tw, float2 *grid, int n_sf,
+                       cudaStream_t stream)
+{
+    const int blocks = n_sf * 16;
+    switch (P.N) {
+    case 2048: ofdm_demod_r16_kernel<2048, T><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    case 1024: ofdm_demod_r16_kernel<1024, T><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    case 512:  ofdm_demod_r16_kernel<512, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    case 256:  ofdm_demod_r16_kernel<256, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    default:   ofdm_demod_r16_kernel<128, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    }
+}
+
 }  // namespace
 
 struct FftTwiddles { float2 *tw; };
@@ -140,13 +287,16 @@ int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long 
     float2 *tw = nullptr;
     int rc = get_twiddles(ctx, P.N, &tw);
     if (rc) return rc;
+    const bool radix4 = getenv("LTEB200_FFT_RADIX4") != nullptr;   // the shared-memory radix-4 kernel (bit-identical to the oracle's FFT shim)
     const int threads = P.N / 4 < 64 ? 64 : (P.N / 4 > 512 ? 512 : P.N / 4);
     const size_t smem = sizeof(float2) * 2 * P.N;
-    if (iq_fmt == LTEB200_IQ_F32)
-        ofdm_demod_kernel<float2, false><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
-    else if (iq_fmt == LTEB200_IQ_I8)
-        ofdm_demod_kernel<char2, false><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
-    else { lteb200_set_error(ctx, "unknown I/Q format %d", iq_fmt); return LTEB200_ERR_ARGS; }
+    if (iq_fmt == LTEB200_IQ_F32) {
+        if (radix4) ofdm_demod_kernel<float2, false><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        else launch_r16<float2>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid, n_sf, stream);
+    } else if (iq_fmt == LTEB200_IQ_I8) {
+        if (radix4) ofdm_demod_kernel<char2, false><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        else launch_r16<char2>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid, n_sf, stream);
+    } else { lteb200_set_error(ctx, "unknown I/Q format %d", iq_fmt); return LTEB200_ERR_ARGS; }
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;
