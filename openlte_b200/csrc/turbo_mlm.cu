@@ -8,7 +8,7 @@
 // restated on the CPU in oracle/port/turbo_mlm.cc (the bit-exact twin the tests compare against).
 //
 // B200 mapping: one CTA per code block, everything of the block resident in shared memory for all iterations
-// (LLRs int8, extrinsics int16, forward metrics of every step int16, interleaver tables: 222 KB at K = 6144, so one CTA of
+// (LLRs int8, extrinsics int16, forward metrics of every step int16, interleaver tables: 198 KB at K = 6144, so one CTA of
 // 384 threads per SM); one thread per 16-step window holds the 8 forward/backward state metrics in
 // registers (int32, DPX add-max), windows are coupled by state-metric propagation from the previous
 // iteration, so all K/32 windows of a block advance in parallel without warm-up recursions.  Shared-memory
@@ -49,7 +49,10 @@ __device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) 
 // Predecessors of state d are 2(d&3) and 2(d&3)+1, so the even/odd split makes every add-compare-select a vertical
 // 16x2 operation; one byte-permute per register restores the layout for the next step.
 struct Pass {
-    const int16_t *Lsa;   // systematic + a-priori LLR (window-transposed), prepared before the pass
+    const int8_t *Ls;     // systematic LLRs (window-transposed, natural order)
+    const int16_t *LeSrc; // extrinsic of the OTHER constituent decoder (its own order)
+    const uint16_t *piT;  // second decoder: position of pi(k) for the position of k
+    const uint16_t *cs, *cp;  // first decoder: CSR lists of the positions that de-interleave onto a position
     const int8_t *Lp;
     int16_t *LeOut;
     uint4 *st;            // [WIN][nw] forward metrics of every step (raw, 8 x int16)
@@ -91,7 +94,29 @@ __device__ __forceinline__ int bwd_step(uint32_t &ba, uint32_t &bb, uint32_t &bc
     return clampi(((L - ls) * 3) >> 2, -LE_LIM, LE_LIM);
 }
 
-template <int WIN, int NT>
+// systematic + a-priori LLR of position p, computed where it is consumed (no intermediate array, no extra barrier):
+//   second decoder: interleave          Lsa2(p) = Ls[q] + Le1[q],  q = position of pi(k)
+//   first decoder : de-interleave+combine Lsa1(p) = Ls[p] + clamp(sum of Le2 over the positions that map onto p)
+// 0..3 contributions per position for the reference's wrapped interleaver (exactly 1 for every spec-correct block size):
+// the first three are fetched unconditionally (independent loads), the rare rest in a loop.
+__device__ __forceinline__ int la_first(const Pass &P, int p)
+{
+    const int t0 = P.cs[p], cnt = (int)P.cs[p + 1] - t0;
+    const int i0 = P.cp[t0], i1 = P.cp[t0 + 1], i2 = P.cp[t0 + 2];
+    const int v0 = P.LeSrc[i0], v1 = P.LeSrc[i1], v2 = P.LeSrc[i2];
+    int acc = (cnt > 0 ? v0 : 0) + (cnt > 1 ? v1 : 0) + (cnt > 2 ? v2 : 0);
+#pragma unroll 1
+    for (int t = t0 + 3; t < t0 + cnt; t++) acc += (int)P.LeSrc[P.cp[t]];
+    return clampi(acc, -LA_LIM, LA_LIM);
+}
+template <bool SECOND>
+__device__ __forceinline__ int lsa_of(const Pass &P, int p)
+{
+    if (SECOND) { const int q = P.piT[p]; return (int)P.Ls[q] + (int)P.LeSrc[q]; }
+    return (int)P.Ls[p] + la_first(P, p);
+}
+
+template <int WIN, int NT, bool SECOND>
 __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
 {
     const bool active = w < nw;
@@ -124,7 +149,6 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
     }
     __syncthreads();  // every boundary of the previous iteration is read before any is overwritten
 
-    const int16_t *Lsa = P.Lsa + w;
     const int8_t *Lp = P.Lp + w;
     uint4 *st = P.st + w;
     int16_t *Le = P.LeOut + w;
@@ -133,7 +157,7 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
         // up front (they do not depend on the recursion) so that no shared-memory latency sits on the dependent chain.
         uint32_t in[WIN];
 #pragma unroll
-        for (int i = 0; i < WIN; i++) in[i] = pk((int)Lsa[i * NT], (int)Lp[i * NT]);   // (Lsa, Lp)
+        for (int i = 0; i < WIN; i++) in[i] = pk(lsa_of<SECOND>(P, i * NT + w), (int)Lp[i * NT]);   // (Lsa, Lp)
 #pragma unroll
         for (int i = 0; i < WIN; i++) {
             st[i * NT] = make_uint4(e01, e23, o01, o23);
@@ -155,12 +179,14 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
         // ---- the short last window of block sizes that are not a multiple of WIN
         for (int i = 0; i < n; i++) {
             st[i * NT] = make_uint4(e01, e23, o01, o23);
-            if ((i & 3) == 0) fwd_step<WIN, NT, true>(e01, e23, o01, o23, Lsa[i * NT], Lp[i * NT]);
-            else fwd_step<WIN, NT, false>(e01, e23, o01, o23, Lsa[i * NT], Lp[i * NT]);
+            const int ls = lsa_of<SECOND>(P, i * NT + w);
+            if ((i & 3) == 0) fwd_step<WIN, NT, true>(e01, e23, o01, o23, ls, Lp[i * NT]);
+            else fwd_step<WIN, NT, false>(e01, e23, o01, o23, ls, Lp[i * NT]);
         }
         for (int i = n - 1; i >= 0; i--) {
-            if ((i & 3) == 3) Le[i * NT] = (int16_t)bwd_step<true>(ba, bb, bc, bd, st[i * NT], Lsa[i * NT], Lp[i * NT]);
-            else Le[i * NT] = (int16_t)bwd_step<false>(ba, bb, bc, bd, st[i * NT], Lsa[i * NT], Lp[i * NT]);
+            const int ls = lsa_of<SECOND>(P, i * NT + w);
+            if ((i & 3) == 3) Le[i * NT] = (int16_t)bwd_step<true>(ba, bb, bc, bd, st[i * NT], ls, Lp[i * NT]);
+            else Le[i * NT] = (int16_t)bwd_step<false>(ba, bb, bc, bd, st[i * NT], ls, Lp[i * NT]);
         }
         if (w > 0) P.bB[w - 1] = make_uint4(ba, bb, bc, bd);
     }
@@ -187,8 +213,8 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     uint4 *st = (uint4 *)smem_raw;                                  // 16*NP bytes
     uint4 *bA1 = (uint4 *)(smem_raw + (size_t)16 * NP);             // 4 x nw uint4
     uint4 *bB1 = bA1 + NT, *bA2 = bB1 + NT, *bB2 = bA2 + NT;
-    int16_t *Lsa1 = (int16_t *)(bB2 + NT);                          // Ls + a-priori of decoder 1 (natural order)
-    int16_t *Lsa2 = Lsa1 + NP, *Le1 = Lsa2 + NP, *Le2 = Le1 + NP;
+    int16_t *Le1 = (int16_t *)(bB2 + NT);                           // extrinsics of the two constituent decoders
+    int16_t *Le2 = Le1 + NP;
     uint16_t *s_piT = (uint16_t *)(Le2 + NP);                       // interleaver and its CSR inverse, staged once per block
     uint16_t *s_cs = s_piT + NP, *s_cp = s_cs + (NP + 2);
     int8_t *Ls = (int8_t *)(s_cp + NP + 2);
@@ -293,13 +319,13 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     __syncthreads();
     const float maxv = s_red[0];
     // ---- quantise into the window-transposed arrays (thread w writes column w: conflict free); padding stays zero
-    for (int p = tid; p < NP; p += nt) { Lsa2[p] = 0; Le1[p] = 0; Le2[p] = 0; }
+    for (int p = tid; p < NP; p += nt) { Le1[p] = 0; Le2[p] = 0; }
     if (tid < NT) {
 #pragma unroll
         for (int i = 0; i < WIN; i++) {
             const int p = i * NT + tid;
             const int q0 = (i < nown) ? qf(v[3 * i], maxv) : 0, q1 = (i < nown) ? qf(v[3 * i + 1], maxv) : 0, q2 = (i < nown) ? qf(v[3 * i + 2], maxv) : 0;
-            Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2; Lsa1[p] = (int16_t)q0;
+            Ls[p] = (int8_t)q0; Lp1[p] = (int8_t)q1; Lp2[p] = (int8_t)q2;
         }
     }
     if (tid < 12) s_tail[tid] = qf(tail_v, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
@@ -311,8 +337,8 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     __syncthreads();
 
     Pass P1, P2;
-    P1.Lsa = Lsa1; P1.Lp = Lp1; P1.LeOut = Le1; P1.st = st; P1.bA = bA1; P1.bB = bB1;
-    P2.Lsa = Lsa2; P2.Lp = Lp2; P2.LeOut = Le2; P2.st = st; P2.bA = bA2; P2.bB = bB2;
+    P1.Ls = Ls; P1.LeSrc = Le2; P1.piT = s_piT; P1.cs = s_cs; P1.cp = s_cp; P1.Lp = Lp1; P1.LeOut = Le1; P1.st = st; P1.bA = bA1; P1.bB = bB1;
+    P2.Ls = Ls; P2.LeSrc = Le1; P2.piT = s_piT; P2.cs = s_cs; P2.cp = s_cp; P2.Lp = Lp2; P2.LeOut = Le2; P2.st = st; P2.bA = bA2; P2.bB = bB2;
     // tail multiplexing (liblte_phy.cc:10575-10586): x = systematic/feedback bits, z = parity bits of the 3 tail steps
     P1.xt[0] = s_tail[0]; P1.xt[1] = s_tail[2]; P1.xt[2] = s_tail[4];
     P1.zt[0] = s_tail[1]; P1.zt[1] = s_tail[3]; P1.zt[2] = s_tail[5];
@@ -320,28 +346,13 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     P2.zt[0] = s_tail[7]; P2.zt[1] = s_tail[9]; P2.zt[2] = s_tail[11];
 
     for (int it = 0; it < n_iter; it++) {
-        dec_pass<WIN, NT>(P1, tid, nw, K);
-        for (int p = tid; p < NP; p += nt) { const int q = s_piT[p]; Lsa2[p] = (int16_t)((int)Ls[q] + (int)Le1[q]); }   // interleave
-        __syncthreads();
-        dec_pass<WIN, NT>(P2, tid, nw, K);
-#pragma unroll 4
-        for (int p = tid; p < NP; p += nt) {                                                        // de-interleave, combine
-            // 0..3 contributions per position for the reference's wrapped interleaver (exactly 1 for every spec-correct size):
-            // the first three are fetched unconditionally (independent loads), the rare rest in a loop
-            const int t0 = s_cs[p], cnt = (int)s_cs[p + 1] - t0;
-            const int i0 = s_cp[t0], i1 = s_cp[t0 + 1], i2 = s_cp[t0 + 2];
-            const int v0 = Le2[i0], v1 = Le2[i1], v2 = Le2[i2];
-            int acc = (cnt > 0 ? v0 : 0) + (cnt > 1 ? v1 : 0) + (cnt > 2 ? v2 : 0);
-#pragma unroll 1
-            for (int t = t0 + 3; t < t0 + cnt; t++) acc += (int)Le2[s_cp[t]];
-            Lsa1[p] = (int16_t)((int)Ls[p] + clampi(acc, -LA_LIM, LA_LIM));
-        }
-        __syncthreads();
+        dec_pass<WIN, NT, false>(P1, tid, nw, K);
+        dec_pass<WIN, NT, true>(P2, tid, nw, K);
     }
     if (!FUSED) {
         for (int j = tid; j < K; j += nt) {
             const int p = (j % WIN) * NT + (j / WIN);
-            out[(size_t)cb * K + j] = ((int)Lsa1[p] + (int)Le1[p] >= 0) ? 0 : 1;
+            out[(size_t)cb * K + j] = ((int)Ls[p] + la_first(P1, p) + (int)Le1[p] >= 0) ? 0 : 1;
         }
     } else {
         // dlsch_channel_decode's tail (liblte_phy.cc:12841-12869): drop the F filler bits, CRC24A over [a | p], emit a.
@@ -358,7 +369,7 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
 #pragma unroll
             for (int i = 0; i < WIN; i++) {
                 const int p = i * NT + tid;
-                const int bit = (i < nown_e && ((int)Lsa1[p] + (int)Le1[p] < 0)) ? 1 : 0;
+                const int bit = (i < nown_e && ((int)Ls[p] + la_first(P1, p) + (int)Le1[p] < 0)) ? 1 : 0;
                 packed[i >> 3] |= (unsigned long long)bit << (8 * (i & 7));
             }
             const int idx0 = WIN * tid - A.F;                              // index of this thread's first bit inside [a | p]
@@ -439,7 +450,7 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
             ctx->mlm[K] = mt;
         } else mt = it->second;
     }
-    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)4 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
+    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)2 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
     const int threads = ((nw + 31) / 32) * 32;
     if (fused) {
         LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
