@@ -215,7 +215,7 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
         LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
         LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
-    int chunk = n_sf / 8;
+    int chunk = n_sf / 16;
     if (const char *e = getenv("LTEB200_E2E_CHUNK")) chunk = atoi(e);
     if (chunk < 64) chunk = 64;
     if (chunk > n_sf) chunk = n_sf;
