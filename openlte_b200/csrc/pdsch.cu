@@ -306,7 +306,13 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
     }
     // ---- fused path: one kernel per group of allocations with equal K does demod + unmatch + decode + CRC per transport block
-    if (turbo_mode == LTEB200_TURBO_MAXLOGMAP && N_ant == 1 && !getenv("LTEB200_NO_FUSE")) {
+    bool fusable = turbo_mode == LTEB200_TURBO_MAXLOGMAP && N_ant == 1 && !getenv("LTEB200_NO_FUSE");
+    for (int a = 0; a < n_alloc && fusable; a++) {
+        // the fused kernel stages an allocation's soft bits in the shared memory of its forward-metric store: 64 floats per window column
+        const int nw = (T[a].K + 15) / 16, NT = nw <= 64 ? 64 : (nw <= 128 ? 128 : 384);
+        if (T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;
+    }
+    if (fusable) {
         int *d_sn = nullptr;
         rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, stream);
         if (rc) return rc;

@@ -200,14 +200,14 @@ __device__ __forceinline__ void dec_pass(const Pass &P, int w, int nw, int K)
 //                 descrambling into shared memory (aliasing the forward-metric store, which is idle until the first pass),
 //                 rate unmatching through the gather map straight into each thread's window, decoding, then CRC24A and
 //                 transport-block extraction from the decisions.  Block index = local_alloc * n_sf + subframe.
-template <int WIN, bool FUSED>
-__global__ void __launch_bounds__(WIN == 32 ? 192 : 384)
+template <int WIN, int NT, bool FUSED>
+__global__ void __launch_bounds__(NT)
 turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_t *__restrict__ piT,
                  const uint16_t *__restrict__ csr_start, const uint16_t *__restrict__ csr_pos, uint8_t *__restrict__ out,
                  const __grid_constant__ FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = 6144 / WIN;   // row stride of the window-transposed arrays (compile-time: largest block size)
+    // NT: row stride of the window-transposed arrays = the largest window count of this size class (compile-time)
     const int nw = (K + WIN - 1) / WIN;
     constexpr int NP = WIN * NT;     // padded length
     uint4 *st = (uint4 *)smem_raw;                                  // 16*NP bytes
@@ -425,8 +425,9 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
     int rc = lteb200_get_qpp(ctx, K, &qt);  // validates K
     if (rc) return rc;
     constexpr int WIN = MLM_WIN;
-    constexpr int NT = 6144 / WIN, NP = WIN * NT;
     const int nw = (K + WIN - 1) / WIN;
+    // size class: shared memory (and therefore blocks per SM) scales with the block size
+    const int NT = nw <= 64 ? 64 : (nw <= 128 ? 128 : 6144 / WIN), NP = WIN * NT;
     MlmTables mt;
     {
         auto it = ctx->mlm.find(K);
@@ -452,15 +453,17 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
     }
     const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)2 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
     const int threads = ((nw + 31) / 32) * 32;
-    if (fused) {
-        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        turbo_mlm_kernel<WIN, true><<<n_cb, threads, smem, stream>>>(nullptr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, nullptr, *fused);
-    } else {
-        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FusedParams none;
-        memset(&none, 0, sizeof(none));
-        turbo_mlm_kernel<WIN, false><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits, none);
-    }
+    FusedParams none;
+    memset(&none, 0, sizeof(none));
+    const FusedParams &fp = fused ? *fused : none;
+#define MLM_LAUNCH(NT_, FUSED_)                                                                                                     \
+    do {                                                                                                                            \
+        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, NT_, FUSED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        turbo_mlm_kernel<WIN, NT_, FUSED_><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits, fp); \
+    } while (0)
+    if (fused) { if (NT == 64) MLM_LAUNCH(64, true); else if (NT == 128) MLM_LAUNCH(128, true); else MLM_LAUNCH(6144 / WIN, true); }
+    else       { if (NT == 64) MLM_LAUNCH(64, false); else if (NT == 128) MLM_LAUNCH(128, false); else MLM_LAUNCH(6144 / WIN, false); }
+#undef MLM_LAUNCH
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;

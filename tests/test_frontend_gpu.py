@@ -220,3 +220,25 @@ def test_host_pointer_pipeline_equals_device_path(ctx):
             h_tb[:] = 7; h_ok[:] = 0
     finally:
         os.environ.pop("LTEB200_E2E_CHUNK", None)
+
+
+def test_wide_allocation_falls_back_to_staged_kernels(ctx):
+    """An allocation whose soft bits do not fit the fused kernel's shared-memory staging area (100 PRB, 64QAM: 82,800 bits for one
+    K = 6144 block) must still decode (staged kernels), and small block sizes take the small-footprint instantiation."""
+    import torch
+    from openlte_b200 import synth
+    cell = 9
+    for allocs in ([dict(mod=3, prb=list(range(100)), tbs=6120, rnti=0x51)], [dict(mod=1, prb=list(range(3, 9)), tbs=256, rnti=0x52)]):
+        n_sf = 3
+        tx = synth.make_subframes(n_sf, allocs, N_id_cell=cell, seed=2, first_subfr=1)
+        stream = np.concatenate([tx["samples"].reshape(-1), synth.crs_only_tail(100, cell, 4, 4)])
+        iq = np.stack([stream.real, stream.imag], -1).astype(np.float32)
+        d_iq = torch.from_numpy(iq).cuda()
+        start = (np.arange(n_sf) * 30720).astype(np.int64); sn = tx["subfr_nums"].astype(np.int32)
+        ca = (Alloc * 1)(Alloc.make(allocs[0]["mod"], allocs[0]["prb"], allocs[0]["tbs"], allocs[0]["rnti"]))
+        tbs = allocs[0]["tbs"]
+        tb = torch.zeros((n_sf, 1, tbs), dtype=torch.uint8, device="cuda"); ok = torch.zeros((n_sf, 1), dtype=torch.int32, device="cuda")
+        ctx.check(ctx.lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, start.ctypes.data_as(C.c_void_p), sn.ctypes.data_as(C.c_void_p),
+                                           n_sf, 2, ca, 1, 1, 8, dptr(tb), tbs, dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        assert bool(ok.all()) and np.array_equal(tb.cpu().numpy()[:, 0], tx["tb"][0])

@@ -109,3 +109,36 @@ def test_bad_arguments(ctx):
     d = torch.zeros(3 * 47, device="cuda"); o = torch.zeros(64, dtype=torch.uint8, device="cuda")
     assert ctx.lib.turbo_decode_batch(ctx.h, dptr(d), 43, 1, 0, 0, dptr(o), None) == -1   # 43 is not a block size
     assert ctx.lib.turbo_decode_batch(ctx.h, None, 40, 1, 0, 0, dptr(o), None) == -1
+
+
+def test_every_legal_block_size(ctx, port):
+    """All 188 sizes of 36.212 table 5.1.3-3 (including the 20 whose interleaver the reference's uint32 arithmetic breaks):
+    one noisy and one clean block each, both decoders, against the oracle."""
+    import re, os
+    rows = re.findall(r"\{\s*(\d+),\s*(\d+),\s*(\d+)\}", open(os.path.join(os.path.dirname(__file__), "..", "openlte_b200", "csrc", "qpp_table.h")).read())
+    Ks = [int(r[0]) for r in rows]
+    assert len(Ks) == 188
+    rng = np.random.default_rng(2024)
+    for K in Ks:
+        blocks = [noisy_codeword(port, K, s, rng)[1] for s in (0.0, 0.6)]
+        xs = np.stack(blocks)
+        a = gpu_decode(ctx, xs, K, 0)
+        b = gpu_decode(ctx, xs, K, 1, 4)
+        for i in range(2):
+            assert np.array_equal(a[i], port.turbo_decode_ref(xs[i])), f"mode A, K={K}"
+            assert np.array_equal(b[i], port.turbo_decode_mlm(xs[i], 4)), f"mode B, K={K}"
+
+
+def test_empty_and_degenerate_batches(ctx):
+    import torch
+    d = torch.zeros((4, 3 * 44), device="cuda"); o = torch.full((4, 40), 7, dtype=torch.uint8, device="cuda")
+    assert ctx.lib.turbo_decode_batch(ctx.h, dptr(d), 40, 0, 0, 0, dptr(o), None) == 0      # n_cb = 0: nothing to do, nothing touched
+    assert bool((o == 7).all())
+    for mode in (0, 1):                                                                     # all-zero LLRs (max_value = 0 -> NaN -> 0 as on x86)
+        ctx.check(ctx.lib.turbo_decode_batch(ctx.h, dptr(d), 40, 4, mode, 2, dptr(o), None))
+        torch.cuda.synchronize()
+        assert bool((o == 0).all())
+    s = torch.full((2, 3 * 44), 10000.0, device="cuda")                                     # everything punctured
+    ctx.check(ctx.lib.turbo_decode_batch(ctx.h, dptr(s), 40, 2, 0, 0, dptr(o[:2]), None))
+    torch.cuda.synchronize()
+    assert bool((o[:2] == 0).all())

@@ -1,0 +1,79 @@
+"""BASELINE config 5: bandwidth x modulation sweep through the whole receive chain on one GPU (development / reporting
+aid; bench.py is the contract benchmark).  For every (bandwidth, modulation) the band is cut into equal allocations, each a
+single-code-block transport block with the largest K for which G >= 3(K+4) in every subframe class -- the envelope in which
+the reference itself decodes.  Prints one JSON line per configuration."""
+import sys, os, json, ctypes as C, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import openlte_b200
+from openlte_b200 import synth
+from openlte_b200.lib import Alloc
+
+BW = {"1.4": (6, 0), "5": (25, 2), "10": (50, 3), "20": (100, 4)}
+MODS = {"QPSK": 1, "16QAM": 2, "64QAM": 3}
+QM = {1: 2, 2: 4, 3: 6}
+TABLE_K = [k for lo, hi, st in ((40, 512, 8), (528, 1024, 16), (1056, 2048, 32), (2112, 6144, 64)) for k in range(lo, hi + 1, st)]
+
+
+def plan(n_rb, mod, cell, cfi):
+    """equal PRB groups; K = largest table size with 3(K+4) <= min_G over subframe classes, capped at 6144"""
+    qm = QM[mod]
+    best = None
+    for n_alloc in range(1, n_rb + 1):
+        if n_rb % n_alloc:
+            continue
+        per = n_rb // n_alloc
+        groups = [list(range(a * per, (a + 1) * per)) for a in range(n_alloc)]
+        gmin = min(synth.re_indices(n_rb, cell, sn, cfi, g).shape[0] * qm for g in groups for sn in (0, 5, 1))
+        ks = [k for k in TABLE_K if 3 * (k + 4) <= gmin]
+        if not ks:
+            break
+        k = ks[-1]
+        if best is None or k * n_alloc > best[0]:
+            best = (k * n_alloc, k, groups)
+        if k == 6144:
+            continue
+    return best[1], best[2]
+
+
+def main():
+    n_sf = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    L = openlte_b200.load(); ctx = L.new_ctx(0)
+    cell, cfi = 42, 2
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for bw, (n_rb, fs_idx) in BW.items():
+        for mname, mod in MODS.items():
+            K, groups = plan(n_rb, mod, cell, cfi)
+            allocs = [dict(mod=mod, prb=g, tbs=K - 24, rnti=0x300 + i) for i, g in enumerate(groups)]
+            seg = 20
+            tx = synth.make_subframes(seg, allocs, N_id_cell=cell, N_rb_dl=n_rb, fs_idx=fs_idx, cfi=cfi, seed=7, first_subfr=1)
+            n_s = 1920 << fs_idx
+            stream = np.tile(tx["samples"].reshape(-1), -(-n_sf // seg))[: n_sf * n_s]
+            stream = np.concatenate([stream, synth.crs_only_tail(n_rb, cell, (1 + n_sf) % 10, fs_idx)[: 4 * (128 << fs_idx)]])
+            sc = 100.0 / max(np.abs(stream.real).max(), np.abs(stream.imag).max())
+            iq = np.stack([np.rint(stream.real * sc), np.rint(stream.imag * sc)], -1).astype(np.int8)
+            d_iq = torch.from_numpy(iq).cuda()
+            start = (np.arange(n_sf, dtype=np.int64) * n_s); sn = ((1 + np.arange(n_sf)) % 10).astype(np.int32)
+            ca = (Alloc * len(allocs))(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+            tb = torch.zeros((n_sf, len(allocs), K - 24), dtype=torch.uint8, device="cuda"); ok = torch.zeros((n_sf, len(allocs)), dtype=torch.int32, device="cuda")
+            res = {}
+            for mode, name in ((1, "maxlogmap_x8"), (0, "ref_exact")):
+                run = lambda: ctx.check(L.dl_receive_batch(ctx.h, C.c_void_p(d_iq.data_ptr()), 1, iq.shape[0], fs_idx, n_rb, cell, 1, p(start), p(sn), n_sf, cfi,
+                                                           ca, len(allocs), mode, 8, C.c_void_p(tb.data_ptr()), K - 24, C.c_void_p(ok.data_ptr()), None))
+                for _ in range(2):
+                    run()
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    run()
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                want = np.stack(tx["tb"], 1)[np.arange(n_sf) % seg]
+                res[name] = dict(ms_per_step=round(ms, 3), subframes_per_s=round(n_sf / ms * 1e3, 1), crc_pass=float(ok.float().mean().item()),
+                                 bits_ok=bool(np.array_equal(tb.cpu().numpy(), want)))
+            print(json.dumps(dict(bandwidth_MHz=bw, N_rb_dl=n_rb, modulation=mname, n_alloc=len(allocs), prb_per_alloc=len(groups[0]), K=K, n_sf=n_sf, **res)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
