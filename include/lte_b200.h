@@ -168,6 +168,17 @@ int lteb200_find_sss(lteb200_ctx *ctx, const float *i_samps, const float *q_samp
                      int N_rb_dl, uint32_t N_id_2, uint32_t *symb_starts /*[7] in/out*/, float pss_thresh,
                      uint32_t *N_id_1, uint32_t *frame_start_idx);
 
+/* -------------------------------------------------------------------------------------------- front end */
+/* LTE_fdd_dl_fs_samp_buf::freq_shift (LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713) and the int8 -> float
+ * conversion of copy_input_to_samp_buf (:657-694).  d_iq_in: DEVICE samples in iq_fmt; d_iq_out: DEVICE float2 [n_samps].
+ * Sample i is multiplied by exp(-j*2*pi*freq_offset_hz*(index_base+i+1)/fs) exactly as the reference computes it. */
+int lteb200_freq_shift_batch(lteb200_ctx *ctx, const void *d_iq_in, int iq_fmt, long long n_samps, long long index_base,
+                             float freq_offset_hz, int fs_idx, float *d_iq_out, void *stream);
+/* Host twin: in place on the split float buffers, samples [start_idx, start_idx + num_samps). */
+int lteb200_freq_shift(lteb200_ctx *ctx, float *i_buf, float *q_buf, uint32_t start_idx, uint32_t num_samps, float freq_offset, int fs_idx);
+/* Fused form: the OFDM demodulator applies the shift while loading samples (no extra pass over the data). */
+int lteb200_set_freq_offset(lteb200_ctx *ctx, float freq_offset_hz, long long index_base);
+
 /* --------------------------------------------------------------------------------------------- utilities */
 /* Pseudo-random sequence c(n), generate_prs_c (liblte_phy.cc:9669-9704); d_c DEVICE [len] bytes. */
 int lteb200_prs_c_batch(lteb200_ctx *ctx, uint32_t c_init, int len, uint8_t *d_c, void *stream);

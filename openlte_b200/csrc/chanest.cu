@@ -109,7 +109,7 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
     // 4. time interpolation, polar -> Cartesian
     float2 *out = ce + ((size_t)sf * P.N_ant + p) * 14 * P.nsc;
     for (int j = threadIdx.x; j < P.nsc; j += blockDim.x) {
-        auto put = [&](int z, float m, float a) { out[z * P.nsc + j] = make_float2(__fmul_rn(m, cosf(a)), __fmul_rn(m, sinf(a))); };
+        auto put = [&](int z, float m, float a) { float sn_, cs_; sincosf(a, &sn_, &cs_); out[z * P.nsc + j] = make_float2(__fmul_rn(m, cs_), __fmul_rn(m, sn_)); };
         float mg[5], an[5];
 #pragma unroll
         for (int i = 0; i < 5; i++) { mg[i] = Mg[i * 1200 + j]; an[i] = Ag[i * 1200 + j]; }

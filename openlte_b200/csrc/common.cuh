@@ -48,6 +48,8 @@ struct lteb200_ctx {
     std::map<int, MlmTables> mlm;
     std::map<std::vector<int>, RateUnmatchMap> rum;
     cudaStream_t s_h2d, s_comp, s_d2h;   // pipeline streams of the host-pointer entry point (lazily created)
+    float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)
+    long long    cfo_base;
     uint32_t    *crc24a_tab;   // x^j mod g(CRC24A) for j < 6168 (lazily built)
     // statistics
     unsigned long long launches;

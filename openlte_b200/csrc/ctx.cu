@@ -34,6 +34,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->arena_bytes = 0;
     c->launches = 0;
     c->crc24a_tab = nullptr;
+    c->cfo_hz = 0.f; c->cfo_base = 0;
     c->s_h2d = c->s_comp = c->s_d2h = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,

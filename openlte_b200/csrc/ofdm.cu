@@ -16,7 +16,21 @@ struct OfdmParams {
     int N, log2N, cp0, cpe, slot;   // FFT size, CP lengths, samples per slot
     int h;                          // 6*N_rb_dl
     int nsc;                        // 12*N_rb_dl (grid row length)
+    // front-end frequency shift fused into the sample load (LTE_fdd_dl_fs_samp_buf::freq_shift, fs.cc:696-713); 0 = off
+    float cfo_hz;
+    double cfo_fs;                  // sample rate in Hz
+    long long cfo_base;             // stream index of d_iq[0] in the caller's buffer numbering
 };
+
+// one sample of freq_shift(): phase = (i+1)*freq_offset (float product) * 2*pi / fs (double), cosf/sinf of the float-rounded phase
+__device__ __forceinline__ float2 cfo_rotate(float2 v, long long i, float f_hz, double fs)
+{
+    const float t = __fmul_rn((float)(unsigned)(i + 1), f_hz);
+    const float ph = (float)((double)t * 2.0 * 3.14159265358979323846 / fs);
+    float sn, cs;
+    sincosf(ph, &sn, &cs);
+    return make_float2(__fadd_rn(__fmul_rn(v.x, cs), __fmul_rn(v.y, sn)), __fsub_rn(__fmul_rn(v.y, cs), __fmul_rn(v.x, sn)));
+}
 
 template <typename T> __device__ __forceinline__ float2 load_iq(const T *p, long long i);
 template <> __device__ __forceinline__ float2 load_iq<float2>(const float2 *p, long long i) { return p[i]; }
@@ -49,7 +63,9 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
                                   (l == 0 ? P.cp0 : P.cpe) - 1;
     for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
         const long long s = idx + i;
-        bufA[i] = (s >= 0 && s < n_samps) ? load_iq<T>(iq, s) : make_float2(0.f, 0.f);
+        float2 v = (s >= 0 && s < n_samps) ? load_iq<T>(iq, s) : make_float2(0.f, 0.f);
+        if (P.cfo_hz != 0.f) v = cfo_rotate(v, P.cfo_base + s, P.cfo_hz, P.cfo_fs);
+        bufA[i] = v;
     }
     __syncthreads();
     // Stockham autosort, decimation in frequency.  n = remaining transform length, s = stride.
@@ -152,7 +168,8 @@ template <> struct Dft<16> {
 // to the resource grid through the bin -> subcarrier map (last pass, where p == 0 and no twiddle applies).
 template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID>
 __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long long w0, long long n_samps, const float2 *__restrict__ src,
-                                              float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid)
+                                              float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid,
+                                              float cfo_hz = 0.f, double cfo_fs = 1.0, long long cfo_base = 0)
 {
     constexpr int NTHR = N / 16, s = N / n, n1 = n / R;
 #pragma unroll
@@ -166,6 +183,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
             if (SRC_GLOBAL) {
                 const long long sidx = w0 + i;
                 x[k] = (sidx >= 0 && sidx < n_samps) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
+                if (cfo_hz != 0.f) x[k] = cfo_rotate(x[k], cfo_base + sidx, cfo_hz, cfo_fs);
             } else x[k] = src[i];
         }
         Dft<R>::run(x);
@@ -197,29 +215,29 @@ ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long lo
     float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
     const bool act = tid < N / 16;
     if constexpr (N == 2048) {          // 16 x 16 x 8
-        if (act) stockham_pass<N, 16, 2048, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 2048, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 128, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 1024) {   // 16 x 16 x 4
-        if (act) stockham_pass<N, 16, 1024, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 1024, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 64, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 512) {    // 16 x 8 x 4
-        if (act) stockham_pass<N, 16, 512, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 512, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 8, 32, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 256) {    // 16 x 16
-        if (act) stockham_pass<N, 16, 256, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 256, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 16, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     } else {                  // 128 = 16 x 8
-        if (act) stockham_pass<N, 16, 128, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 128, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     }
@@ -284,6 +302,7 @@ int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long 
     OfdmParams P;
     P.N = 128 << fs_idx; P.log2N = 7 + fs_idx; P.cp0 = 10 << fs_idx; P.cpe = 9 << fs_idx; P.slot = 960 << fs_idx;
     P.h = 6 * N_rb_dl; P.nsc = 12 * N_rb_dl;
+    P.cfo_hz = ctx->cfo_hz; P.cfo_fs = 1920000.0 * (double)(1 << fs_idx); P.cfo_base = ctx->cfo_base;
     float2 *tw = nullptr;
     int rc = get_twiddles(ctx, P.N, &tw);
     if (rc) return rc;
@@ -309,6 +328,7 @@ int fft_windows_launch(lteb200_ctx *ctx, const float *d_iq, long long n_samps, i
     OfdmParams P;
     P.N = 128 << fs_idx; P.log2N = 7 + fs_idx; P.cp0 = 10 << fs_idx; P.cpe = 9 << fs_idx; P.slot = 960 << fs_idx;
     P.h = 6 * N_rb_dl; P.nsc = 12 * N_rb_dl;
+    P.cfo_hz = 0.f; P.cfo_fs = 1.0; P.cfo_base = 0;   // cell search works on samples the caller has already shifted, as in the reference
     float2 *tw = nullptr;
     int rc = get_twiddles(ctx, P.N, &tw);
     if (rc) return rc;
@@ -316,5 +336,72 @@ int fft_windows_launch(lteb200_ctx *ctx, const float *d_iq, long long n_samps, i
     ofdm_demod_kernel<float2, true><<<n_win, threads, sizeof(float2) * 2 * P.N, stream>>>((const float2 *)d_iq, n_samps, d_win_start, P, tw, (float2 *)d_out);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}
+
+// ---- standalone front end: int8 -> float de-interleave is implicit (char2 loads); frequency shift of a whole buffer
+namespace {
+template <typename T>
+__global__ void freq_shift_kernel(const T *__restrict__ in, long long n, long long index_base, float f_hz, double fs, float2 *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 v = load_iq<T>(in, i);
+    if (f_hz != 0.f) v = cfo_rotate(v, index_base + i, f_hz, fs);
+    out[i] = v;
+}
+__global__ void freq_shift_split_kernel(float *__restrict__ is, float *__restrict__ qs, long long n, long long index_base, float f_hz, double fs)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 v = cfo_rotate(make_float2(is[i], qs[i]), index_base + i, f_hz, fs);
+    is[i] = v.x; qs[i] = v.y;
+}
+}  // namespace
+
+extern "C" int lteb200_freq_shift_batch(lteb200_ctx *ctx, const void *d_iq_in, int iq_fmt, long long n_samps, long long index_base, float freq_offset_hz,
+                                        int fs_idx, float *d_iq_out, void *stream)
+{
+    if (!ctx || !d_iq_in || !d_iq_out || n_samps < 0 || fs_idx < 0 || fs_idx > 4) return LTEB200_ERR_ARGS;
+    if (n_samps == 0) return LTEB200_OK;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const double fs = 1920000.0 * (double)(1 << fs_idx);
+    const unsigned blocks = (unsigned)((n_samps + 255) / 256);
+    if (iq_fmt == LTEB200_IQ_F32) freq_shift_kernel<float2><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)d_iq_in, n_samps, index_base, freq_offset_hz, fs, (float2 *)d_iq_out);
+    else if (iq_fmt == LTEB200_IQ_I8) freq_shift_kernel<char2><<<blocks, 256, 0, (cudaStream_t)stream>>>((const char2 *)d_iq_in, n_samps, index_base, freq_offset_hz, fs, (float2 *)d_iq_out);
+    else return LTEB200_ERR_ARGS;
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}
+
+// Host twin of LTE_fdd_dl_fs_samp_buf::freq_shift(start_idx, num_samps, freq_offset) (fs.cc:696-713): in place on the split buffers.
+extern "C" int lteb200_freq_shift(lteb200_ctx *ctx, float *i_buf, float *q_buf, uint32_t start_idx, uint32_t num_samps, float freq_offset, int fs_idx)
+{
+    if (!ctx || !i_buf || !q_buf || fs_idx < 0 || fs_idx > 4) return LTEB200_ERR_ARGS;
+    if (num_samps == 0) return LTEB200_OK;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    float *di = nullptr, *dq = nullptr;
+    LTE_CUDA_OK(ctx, cudaMalloc(&di, sizeof(float) * num_samps));
+    LTE_CUDA_OK(ctx, cudaMalloc(&dq, sizeof(float) * num_samps));
+    cudaMemcpy(di, i_buf + start_idx, sizeof(float) * num_samps, cudaMemcpyHostToDevice);
+    cudaMemcpy(dq, q_buf + start_idx, sizeof(float) * num_samps, cudaMemcpyHostToDevice);
+    freq_shift_split_kernel<<<(num_samps + 255) / 256, 256>>>(di, dq, num_samps, start_idx, freq_offset, 1920000.0 * (double)(1 << fs_idx));
+    ctx->launches += 1;
+    cudaMemcpy(i_buf + start_idx, di, sizeof(float) * num_samps, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(q_buf + start_idx, dq, sizeof(float) * num_samps, cudaMemcpyDeviceToHost);
+    cudaFree(di); cudaFree(dq);
+    if (e != cudaSuccess) { lteb200_set_error(ctx, "freq_shift: %s", cudaGetErrorString(e)); return LTEB200_ERR_CUDA; }
+    return LTEB200_OK;
+}
+
+// Frequency offset applied by the OFDM demodulator while it loads samples (the fused form of the above): every later
+// lteb200_get_dl_subframe_and_ce* / lteb200_dl_receive* call on this context rotates sample i of its stream by
+// exp(-j 2 pi f (index_base + i + 1) / fs).  0 Hz switches it off.
+extern "C" int lteb200_set_freq_offset(lteb200_ctx *ctx, float freq_offset_hz, long long index_base)
+{
+    if (!ctx) return LTEB200_ERR_ARGS;
+    ctx->cfo_hz = freq_offset_hz;
+    ctx->cfo_base = index_base;
     return LTEB200_OK;
 }

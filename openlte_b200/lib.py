@@ -58,6 +58,9 @@ SYMBOLS = {
     "lteb200_find_coarse_timing_and_freq_offset": (_i, [_vp, _vp, _vp, _ll, _i, _u32, _vp, _vp, _vp]),
     "lteb200_find_pss_and_fine_timing": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lteb200_find_sss": (_i, [_vp, _vp, _vp, _ll, _i, _i, _u32, _vp, _f, _vp, _vp]),
+    "lteb200_freq_shift_batch": (_i, [_vp, _vp, _i, _ll, _ll, _f, _i, _vp, _vp]),
+    "lteb200_freq_shift": (_i, [_vp, _vp, _vp, _u32, _u32, _f, _i]),
+    "lteb200_set_freq_offset": (_i, [_vp, _f, _ll]),
     "lteb200_prs_c_batch": (_i, [_vp, _u32, _i, _vp, _vp]),
     "lteb200_crc24a_check_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
 }

@@ -105,6 +105,12 @@ def fft_forward(re, im):
     lib().op_fft_forward(int(re.size), _p(re), _p(im), _p(o_re), _p(o_im)); return o_re, o_im
 
 
+def freq_shift(i_buf, q_buf, start_idx, num_samps, freq_offset, fs):
+    i_buf = np.ascontiguousarray(i_buf, np.float32).copy(); q_buf = np.ascontiguousarray(q_buf, np.float32).copy()
+    lib().op_freq_shift(_p(i_buf), _p(q_buf), C.c_uint32(start_idx), C.c_uint32(num_samps), C.c_float(freq_offset), C.c_uint32(fs))
+    return i_buf, q_buf
+
+
 def crs(N_s, L, N_id_cell):
     re = np.zeros(220, np.float32); im = np.zeros(220, np.float32); lib().op_crs(N_s, L, N_id_cell, _p(re), _p(im)); return re, im
 

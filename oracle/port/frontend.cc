@@ -399,3 +399,18 @@ extern "C" int op_pdsch_decode(const float *rx_re, const float *rx_im, const flo
     return op_pdsch_decode_nant(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, 1, subfr, N_pdcch_symbs, mod, N_prb, prb, tbs, rv, rnti, turbo_mode,
                                 n_iter, out_bits, NULL, NULL);
 }
+
+/* ------------------------------------------------------------------------------------------------ front end
+ * LTE_fdd_dl_fs_samp_buf::freq_shift, LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713: the phase is
+ * (i+1)*freq_offset as a FLOAT product, scaled by 2*pi/fs in double, rounded to float by cosf/sinf.  (The member
+ * function lives in the GNU Radio block, which does not build here: this row's parity is pinned on the formula alone.) */
+extern "C" void op_freq_shift(float *i_buf, float *q_buf, uint32_t start_idx, uint32_t num_samps, float freq_offset, uint32_t fs)
+{
+    for (uint32_t i = start_idx; i < start_idx + num_samps; i++) {
+        float f_samp_re = cosf((i + 1) * (freq_offset) * 2 * M_PI / fs);
+        float f_samp_im = sinf((i + 1) * (freq_offset) * 2 * M_PI / fs);
+        float tmp_i = i_buf[i], tmp_q = q_buf[i];
+        i_buf[i] = tmp_i * f_samp_re + tmp_q * f_samp_im;
+        q_buf[i] = tmp_q * f_samp_re - tmp_i * f_samp_im;
+    }
+}

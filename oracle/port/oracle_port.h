@@ -55,6 +55,7 @@ int  op_pdsch_re_indices(int N_rb_dl, int N_id_cell, int N_ant, int subfr_num, i
 void op_fft_forward(int n, const float *in_re, const float *in_im, float *out_re, float *out_im);
 void op_samples_to_symbols_dl(const float *i_samps, const float *q_samps, int fs_idx, int N_rb_dl, uint32_t slot_start,
                               int symbol_offset, float *symb_re, float *symb_im);
+void op_freq_shift(float *i_buf, float *q_buf, uint32_t start_idx, uint32_t num_samps, float freq_offset, uint32_t fs);  /* fs.cc:696-713 */
 void op_crs(int N_s, int L, int N_id_cell, float *re220, float *im220);
 void op_get_dl_subframe_and_ce(const float *i_samps, const float *q_samps, int fs_idx, int N_rb_dl, uint32_t frame_start_idx,
                                int subfr_num, int N_id_cell, int N_ant, float *rx_symb_re /*[16][1200]*/,

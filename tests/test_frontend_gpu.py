@@ -242,3 +242,59 @@ def test_wide_allocation_falls_back_to_staged_kernels(ctx):
                                            n_sf, 2, ca, 1, 1, 8, dptr(tb), tbs, dptr(ok), stream_ptr()))
         torch.cuda.synchronize()
         assert bool(ok.all()) and np.array_equal(tb.cpu().numpy()[:, 0], tx["tb"][0])
+
+
+def test_front_end_freq_shift(ctx, port):
+    """LTE_fdd_dl_fs_samp_buf::freq_shift (fs.cc:696-713) and the int8 -> float conversion (:657-694): device batch form,
+    host twin, and the form fused into the OFDM sample load.  Arithmetic is IEEE-identical to the oracle except cosf/sinf
+    (1-2 ulp): stated tolerance 1e-6 of the sample maximum."""
+    import torch
+    case = _loopback_case("loop_64qam_c0_sf1.npz")
+    fs_idx, n_rb, cell = int(case["fs_idx"]), int(case["N_rb_dl"]), int(case["N_id_cell"])
+    fs = 1920000 * (1 << fs_idx)
+    i0 = case["i"].astype(np.float32); q0 = case["q"].astype(np.float32)
+    n = i0.size
+    f = -3127.25
+    wi, wq = port.freq_shift(i0, q0, 0, n, f, fs)
+    scale = max(np.abs(i0).max(), np.abs(q0).max())
+    # 1. device batch form, float input
+    iq = np.stack([i0, q0], -1)
+    d_in = torch.from_numpy(iq).cuda(); d_out = torch.zeros_like(d_in)
+    ctx.check(ctx.lib.freq_shift_batch(ctx.h, dptr(d_in), 0, n, 0, f, fs_idx, dptr(d_out), stream_ptr()))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert np.abs(out[:, 0] - wi).max() <= 1e-6 * scale and np.abs(out[:, 1] - wq).max() <= 1e-6 * scale
+    gi, gq = out[:, 0].copy(), out[:, 1].copy()
+    # 2. int8 input (the scan's file format) with a non-zero index base
+    i8 = np.clip(np.round(iq / scale * 100), -127, 127).astype(np.int8)
+    fi, fq = port.freq_shift(i8[:, 0].astype(np.float32), i8[:, 1].astype(np.float32), 0, n, f, fs)
+    d8 = torch.from_numpy(i8).cuda()
+    ctx.check(ctx.lib.freq_shift_batch(ctx.h, dptr(d8), 1, n, 0, f, fs_idx, dptr(d_out), stream_ptr()))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert np.abs(out[:, 0] - fi).max() <= 1e-4 and np.abs(out[:, 1] - fq).max() <= 1e-4
+    base = 5000
+    bi, bq = port.freq_shift(i0, q0, base, n - base, f, fs)
+    ctx.check(ctx.lib.freq_shift_batch(ctx.h, dptr(d_in[base:]), 0, n - base, base, f, fs_idx, dptr(d_out), stream_ptr()))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()[:n - base]
+    assert np.abs(out[:, 0] - bi[base:]).max() <= 1e-6 * scale and np.abs(out[:, 1] - bq[base:]).max() <= 1e-6 * scale
+    # 3. host twin, in place on a sub-range like the member function
+    hi, hq = i0.copy(), q0.copy()
+    ctx.check(ctx.lib.freq_shift(ctx.h, hi.ctypes.data_as(C.c_void_p), hq.ctypes.data_as(C.c_void_p), base, n - base, f, fs_idx))
+    assert np.array_equal(hi[:base], i0[:base])
+    assert np.abs(hi - bi).max() <= 1e-6 * scale and np.abs(hq - bq).max() <= 1e-6 * scale
+    # 4. fused into the OFDM demodulator's load: same grid as demodulating the pre-shifted samples
+    shifted = dict(case); shifted["i"] = gi; shifted["q"] = gq
+    g_want, c_want, _, _ = gpu_front(ctx, shifted)
+    ctx.check(ctx.lib.set_freq_offset(ctx.h, f, 0))
+    try:
+        g_got, c_got, _, _ = gpu_front(ctx, case)
+    finally:
+        ctx.check(ctx.lib.set_freq_offset(ctx.h, 0.0, 0))
+    assert np.array_equal(g_got, g_want), "fused shift must reproduce the two-pass result exactly (same arithmetic, same order)"
+    assert np.array_equal(c_got, c_want)
+    # and against the oracle chain: shift then demodulate
+    rx_re, rx_im, _, _ = port.get_dl_subframe_and_ce(wi, wq, fs_idx, n_rb, int(case["frame_start"]), int(case["subfr"]), cell, 1)
+    want_g = (rx_re + 1j * rx_im)[:, :12 * n_rb]
+    assert np.abs(g_got - want_g).max() <= 2e-6 * np.abs(want_g).max()

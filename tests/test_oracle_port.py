@@ -135,3 +135,20 @@ def test_transmit_diversity_against_reference_fixtures(port, name):
                                             int(c["cfi"]), int(c["mod"]), c["prb"], int(c["tbs"]), int(c["rnti"]))
     assert np.array_equal(soft, c["ref_descramb"])
     assert rc == 0 and np.array_equal(bits, c["ref_tb"]) and np.array_equal(bits, c["tb"])
+
+
+def test_freq_shift_restatement(port):
+    """fs.cc:696-713: rotation by exp(-j*2*pi*f*(i+1)/fs); the float product (i+1)*f limits the phase accuracy, so compare
+    with a float64 rotation at 1e-3 and check the properties the scan relies on: power preserved, f then -f is the identity."""
+    rng = np.random.default_rng(5)
+    n, fs, f = 40000, 30720000, 1234.5
+    i0 = rng.standard_normal(n).astype(np.float32); q0 = rng.standard_normal(n).astype(np.float32)
+    i1, q1 = port.freq_shift(i0, q0, 100, n - 300, f, fs)
+    assert np.array_equal(i1[:100], i0[:100]) and np.array_equal(q1[n - 200:], q0[n - 200:])
+    k = np.arange(100, n - 200)
+    want = (i0[k] + 1j * q0[k]) * np.exp(-2j * np.pi * f * (k + 1) / fs)
+    got = i1[k] + 1j * q1[k]
+    assert np.abs(got - want).max() < 1e-3
+    assert np.allclose(np.abs(got), np.abs(i0[k] + 1j * q0[k]), rtol=1e-5, atol=1e-6)
+    i2, q2 = port.freq_shift(i1, q1, 100, n - 300, -f, fs)
+    assert np.abs(i2 - i0).max() < 1e-5 and np.abs(q2 - q0).max() < 1e-5
