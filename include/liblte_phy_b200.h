@@ -136,6 +136,19 @@ LIBLTE_ERROR_ENUM liblte_phy_get_dl_subframe_and_ce(LIBLTE_PHY_STRUCT *phy_struc
 LIBLTE_ERROR_ENUM liblte_phy_pdsch_channel_decode(LIBLTE_PHY_STRUCT *phy_struct, LIBLTE_PHY_SUBFRAME_STRUCT *subframe,
                                                   LIBLTE_PHY_ALLOCATION_STRUCT *alloc, uint32 N_pdcch_symbs, uint32 N_id_cell, uint8 N_ant,
                                                   uint8 *out_bits, uint32 *N_out_bits);
+// ---- control channels (liblte_phy.h:941-947, 967-1013)
+#define LIBLTE_PHY_PDCCH_MAX_ALLOC 6
+typedef enum { LIBLTE_RRC_PHICH_DURATION_NORMAL = 0, LIBLTE_RRC_PHICH_DURATION_EXTENDED } LIBLTE_RRC_PHICH_DURATION_ENUM;
+typedef struct { LIBLTE_PHY_ALLOCATION_STRUCT alloc[LIBLTE_PHY_PDCCH_MAX_ALLOC]; uint32 N_symbs; uint32 N_alloc; } LIBLTE_PHY_PDCCH_STRUCT;
+typedef struct { float n[4]; uint32 k[4]; uint32 cfi; uint32 N_reg; } LIBLTE_PHY_PCFICH_STRUCT;
+typedef struct { float z_re[3]; float z_im[3]; uint32 k[75]; uint32 N_reg; uint8 b[25][8]; bool present[25][8]; } LIBLTE_PHY_PHICH_STRUCT;
+LIBLTE_ERROR_ENUM liblte_phy_bch_channel_decode(LIBLTE_PHY_STRUCT *phy_struct, LIBLTE_PHY_SUBFRAME_STRUCT *subframe, uint32 N_id_cell, uint8 *N_ant,
+                                                uint8 *out_bits, uint32 *N_out_bits, uint8 *offset);
+// N_ant == 1 only (see lte_b200.h); pcfich->cfi, pcfich->N_reg, phich->N_reg, pdcch->N_symbs and the allocation list are filled in
+LIBLTE_ERROR_ENUM liblte_phy_pdcch_channel_decode(LIBLTE_PHY_STRUCT *phy_struct, LIBLTE_PHY_SUBFRAME_STRUCT *subframe, uint32 N_id_cell, uint8 N_ant,
+                                                  float phich_res, LIBLTE_RRC_PHICH_DURATION_ENUM phich_dur, LIBLTE_PHY_PCFICH_STRUCT *pcfich,
+                                                  LIBLTE_PHY_PHICH_STRUCT *phich, LIBLTE_PHY_PDCCH_STRUCT *pdcch);
+
 void liblte_phy_rate_unmatch_turbo(LIBLTE_PHY_STRUCT *phy_struct, float *e_bits, uint32 N_e_bits, uint8 *dummy_bits, uint32 N_dummy_bits,
                                    uint32 N_codeblocks, uint32 tx_mode, uint32 N_soft, uint32 M_dl_harq, LIBLTE_PHY_CHAN_TYPE_ENUM chan_type,
                                    uint32 rv_idx, float *d_bits, uint32 *N_d_bits);

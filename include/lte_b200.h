@@ -33,6 +33,7 @@ extern "C" {
 #define LTEB200_ERR_CUDA     (-2)
 #define LTEB200_ERR_DECODE   (-3)   /* maps to LIBLTE_ERROR_DECODE_FAIL / INVALID_CRC */
 #define LTEB200_ERR_UNSUPPORTED (-4)
+#define LTEB200_ERR_CONTENTS (-5)   /* maps to LIBLTE_ERROR_INVALID_CONTENTS */
 
 #define LTEB200_RX_NULL_BIT  10000.0f
 
@@ -167,6 +168,52 @@ int lteb200_find_pss_and_fine_timing(lteb200_ctx *ctx, const float *i_samps, con
 int lteb200_find_sss(lteb200_ctx *ctx, const float *i_samps, const float *q_samps, long long n_samps, int fs_idx,
                      int N_rb_dl, uint32_t N_id_2, uint32_t *symb_starts /*[7] in/out*/, float pss_thresh,
                      uint32_t *N_id_1, uint32_t *frame_start_idx);
+
+/* ------------------------------------------------------------------------------------- control channels */
+/* PBCH: batched liblte_phy_bch_channel_decode (liblte_phy.h:941-947, liblte_phy.cc:3968-4100).  d_grid: DEVICE [n][16][nsc]
+ * float2 (subframe 0 of n frames), d_ce: DEVICE [n][4][14][nsc] float2 (four ports, as the scan estimates before it knows
+ * N_ant).  Per subframe the 3 x 4 hypotheses (1/2/4 ports x position in the 40 ms period) are decoded in parallel and the
+ * first hit in the reference's search order is reported. */
+typedef struct {
+    int32_t ok;              /* 1 if a hypothesis passed the CRC */
+    int32_t N_ant;           /* 1, 2 or 4 */
+    int32_t offset;          /* SFN mod 4 */
+    uint8_t bits[24];        /* MIB, one bit per byte */
+} lteb200_bch_result;
+int lteb200_bch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int n,
+                             lteb200_bch_result *d_out, void *stream);
+/* Host twin: HOST planes laid out as LIBLTE_PHY_SUBFRAME_STRUCT (rx_symb_* [16][1200], rx_ce_* [4][16][1200]). */
+int lteb200_bch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, const float *rx_symb_im, const float *rx_ce_re,
+                               const float *rx_ce_im, int N_rb_dl, uint32_t N_id_cell, uint8_t *N_ant, uint8_t *out_bits,
+                               uint32_t *N_out_bits, uint8_t *offset);
+
+/* PCFICH + PDCCH common search space: batched liblte_phy_pdcch_channel_decode (liblte_phy.h:1005-1013, liblte_phy.cc:4519-5134)
+ * for N_ant == 1 (for 2 / 4 ports the reference indexes its channel-estimate scratch with the wrong stride and is undefined:
+ * LTEB200_ERR_UNSUPPORTED).  Per subframe: CFI, then the reference's 12 blind decodes -- aggregation level 4 candidates 0-3,
+ * level 8 candidates 0-1, each as DCI 1A then 1C -- with CRC16 checked against SI-, P- and RA-RNTIs.  Slot = 2*candidate + format.
+ * d_ce: DEVICE [n_sf][1][14][nsc] float2; subfr_num: HOST array. */
+typedef struct {
+    int32_t cfi;             /* 0 = PCFICH did not decode (the reference's INVALID_CRC) */
+    int32_t N_symbs;
+    int32_t found[12];
+    int32_t rnti[12];
+    uint8_t bits[12][32];    /* DCI payload, one bit per byte */
+} lteb200_pdcch_raw;
+typedef struct {
+    lteb200_alloc alloc;     /* what lteb200_pdsch_decode_batch consumes */
+    int32_t mcs;
+    int32_t format;          /* 0 = DCI 1A, 1 = DCI 1C */
+} lteb200_dci;
+int lteb200_pdcch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
+                               float phich_res, const int *subfr_num, int n_sf, lteb200_pdcch_raw *d_out, void *stream);
+/* HOST: dci_1a_unpack / dci_1c_unpack (liblte_phy.cc:13273, 13400) over one subframe's raw results, in the reference's order,
+ * at most 6 allocations; return value mirrors the reference's (see control.cu). */
+int lteb200_pdcch_unpack(const lteb200_pdcch_raw *raw, int N_rb_dl, int N_ant, lteb200_dci *allocs, int *N_alloc);
+/* Host twin of liblte_phy_pdcch_channel_decode: HOST planes as LIBLTE_PHY_SUBFRAME_STRUCT. */
+int lteb200_pdcch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, const float *rx_symb_im, const float *rx_ce_re,
+                                 const float *rx_ce_im, int N_rb_dl, uint32_t subfr_num, uint32_t N_id_cell, uint8_t N_ant,
+                                 float phich_res, int phich_dur, uint32_t *cfi, uint32_t *N_symbs, lteb200_dci *allocs,
+                                 uint32_t *N_alloc);
 
 /* -------------------------------------------------------------------------------------------- front end */
 /* LTE_fdd_dl_fs_samp_buf::freq_shift (LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713) and the int8 -> float

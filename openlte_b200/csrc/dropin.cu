@@ -123,6 +123,48 @@ LIBLTE_ERROR_ENUM liblte_phy_pdsch_channel_decode(LIBLTE_PHY_STRUCT *p, LIBLTE_P
     return rc == LTEB200_ERR_ARGS ? LIBLTE_ERROR_INVALID_INPUTS : LIBLTE_ERROR_DECODE_FAIL;
 }
 
+// liblte_phy.cc:3968-4100: INVALID_INPUTS for bad arguments, DECODE_FAIL when none of the 12 hypotheses passes its CRC
+LIBLTE_ERROR_ENUM liblte_phy_bch_channel_decode(LIBLTE_PHY_STRUCT *p, LIBLTE_PHY_SUBFRAME_STRUCT *sf, uint32 N_id_cell, uint8 *N_ant, uint8 *out_bits,
+                                                uint32 *N_out_bits, uint8 *offset)
+{
+    if (!p || !sf || N_id_cell > 503 || !N_ant || !out_bits || !N_out_bits || !offset) return LIBLTE_ERROR_INVALID_INPUTS;
+    const int rc = lteb200_bch_channel_decode(C_(p), &sf->rx_symb_re[0][0], &sf->rx_symb_im[0][0], &sf->rx_ce_re[0][0][0], &sf->rx_ce_im[0][0][0],
+                                              (int)p->N_rb_dl, N_id_cell, N_ant, out_bits, N_out_bits, offset);
+    if (rc == LTEB200_OK) return LIBLTE_SUCCESS;
+    return rc == LTEB200_ERR_ARGS ? LIBLTE_ERROR_INVALID_INPUTS : LIBLTE_ERROR_DECODE_FAIL;
+}
+
+// liblte_phy.cc:4519-5134.  Return value as the reference's: INVALID_CRC when the PCFICH does not decode, INVALID_INPUTS when no DCI
+// passes its CRC (sic), otherwise the result of unpacking the last DCI that did.
+LIBLTE_ERROR_ENUM liblte_phy_pdcch_channel_decode(LIBLTE_PHY_STRUCT *p, LIBLTE_PHY_SUBFRAME_STRUCT *sf, uint32 N_id_cell, uint8 N_ant, float phich_res,
+                                                  LIBLTE_RRC_PHICH_DURATION_ENUM phich_dur, LIBLTE_PHY_PCFICH_STRUCT *pcfich,
+                                                  LIBLTE_PHY_PHICH_STRUCT *phich, LIBLTE_PHY_PDCCH_STRUCT *pdcch)
+{
+    if (!p || !sf || !pcfich || !phich || !pdcch) return LIBLTE_ERROR_INVALID_INPUTS;
+    static lteb200_dci dci[6];
+    uint32 cfi = 0, n_symbs = 0, n_alloc = 0;
+    const int rc = lteb200_pdcch_channel_decode(C_(p), &sf->rx_symb_re[0][0], &sf->rx_symb_im[0][0], &sf->rx_ce_re[0][0][0], &sf->rx_ce_im[0][0][0],
+                                                (int)p->N_rb_dl, sf->num, N_id_cell, N_ant, phich_res, (int)phich_dur, &cfi, &n_symbs, dci, &n_alloc);
+    if (rc == LTEB200_ERR_CUDA || rc == LTEB200_ERR_UNSUPPORTED) return LIBLTE_ERROR_DECODE_FAIL;
+    pcfich->N_reg = 4;
+    phich->N_reg = 3 * (uint32)ceilf(phich_res * ((float)p->N_rb_dl / 8.0f));
+    if (rc == LTEB200_ERR_DECODE) return LIBLTE_ERROR_INVALID_CRC;
+    pcfich->cfi = cfi;
+    pdcch->N_symbs = n_symbs;
+    pdcch->N_alloc = n_alloc;
+    for (uint32 a = 0; a < n_alloc; a++) {
+        LIBLTE_PHY_ALLOCATION_STRUCT *o = &pdcch->alloc[a];
+        const lteb200_alloc *in = &dci[a].alloc;
+        o->pre_coder_type = LIBLTE_PHY_PRE_CODER_TYPE_TX_DIVERSITY;
+        o->mod_type = (LIBLTE_PHY_MODULATION_TYPE_ENUM)in->mod_type;
+        o->tbs = (uint32)in->tbs; o->rv_idx = (uint32)in->rv_idx; o->N_prb = (uint32)in->N_prb; o->tx_mode = (uint32)in->tx_mode;
+        o->N_codewords = 1; o->rnti = (uint16)in->rnti; o->mcs = (uint8)dci[a].mcs;
+        for (int s_ = 0; s_ < 2; s_++) for (int j = 0; j < in->N_prb && j < 110; j++) o->prb[s_][j] = (uint32)in->prb[s_][j];
+    }
+    if (rc == LTEB200_OK) return LIBLTE_SUCCESS;
+    return rc == LTEB200_ERR_CONTENTS ? LIBLTE_ERROR_INVALID_CONTENTS : LIBLTE_ERROR_INVALID_INPUTS;
+}
+
 // liblte_phy.cc:11246-11490 (void: cannot fail; on a device error d_bits is left untouched and *N_d_bits = 0)
 void liblte_phy_rate_unmatch_turbo(LIBLTE_PHY_STRUCT *p, float *e_bits, uint32 N_e_bits, uint8 *dummy_bits, uint32 N_dummy_bits, uint32 N_codeblocks,
                                    uint32 tx_mode, uint32 N_soft, uint32 M_dl_harq, LIBLTE_PHY_CHAN_TYPE_ENUM chan_type, uint32 rv_idx, float *d_bits,

@@ -29,8 +29,6 @@ __device__ __forceinline__ void demap_store(float xr, float xi, int mod, int Qm,
     for (int t = 0; t < Qm; t++) o[t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)c[t]));  // soft * (1 - 2c), :3835
 }
 
-// four-term sums in the reference's left-to-right order
-__device__ __forceinline__ float sum4(float a, float b, float c, float d) { return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d); }
 #define MUL(a, b) __fmul_rn((a), (b))
 
 // re_idx: [3][idx_stride] (symbol*nsc + subcarrier) per subframe class; M_cls[3]; cseq: [10][c_stride] scrambling bits per subframe number.
@@ -62,33 +60,15 @@ pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const fl
         const float xi = __fdiv_rn(__fsub_rn(MUL(y.y, h.x), MUL(y.x, h.y)), nrm);
         demap_store(xr, xi, P.mod, P.Qm, c, o);
     } else if (N_ant == 2) {
-        const float2 y0 = gr[ix[0]], y1 = gr[ix[1]], h0 = cp[ix[0]], h1 = cp[pstride + ix[0]];   // both estimates at the EVEN element (:7696-7699)
-        const float a0 = __fadd_rn(MUL(h0.x, h0.x), MUL(h0.y, h0.y)), a1 = __fadd_rn(MUL(h1.x, h1.x), MUL(h1.y, h1.y));
-        const float n = __fsqrt_rn(__fadd_rn(MUL(a0, a0), MUL(a1, a1)));                        // sic: sqrt(|h0|^4 + |h1|^4)
-        const float x0r = __fdiv_rn(sum4(MUL(h0.x, y0.x), MUL(h0.y, y0.y), MUL(h1.x, y1.x), MUL(h1.y, y1.y)), n);
-        const float x0i = __fdiv_rn(sum4(MUL(h0.x, y0.y), -MUL(h0.y, y0.x), -MUL(h1.x, y1.y), MUL(h1.y, y1.x)), n);
-        const float x1r = __fdiv_rn(sum4(-MUL(h1.x, y0.x), -MUL(h1.y, y0.y), MUL(h0.x, y1.x), MUL(h0.y, y1.y)), n);
-        const float x1i = __fdiv_rn(sum4(MUL(h1.x, y0.y), -MUL(h1.y, y0.x), MUL(h0.x, y1.y), -MUL(h0.y, y1.x)), n);
-        demap_store(x0r, x0i, P.mod, P.Qm, c, o);
-        demap_store(x1r, x1i, P.mod, P.Qm, c + P.Qm, o + P.Qm);
+        float2 x0, x1;
+        sfbc2(gr[ix[0]], gr[ix[1]], cp[ix[0]], cp[pstride + ix[0]], x0, x1);
+        demap_store(x0.x, x0.y, P.mod, P.Qm, c, o);
+        demap_store(x1.x, x1.y, P.mod, P.Qm, c + P.Qm, o + P.Qm);
     } else {
-        const float2 y0 = gr[ix[0]], y1 = gr[ix[1]], y2 = gr[ix[2]], y3 = gr[ix[3]];
-        const float2 h0 = cp[ix[0]], h2 = cp[2 * pstride + ix[0]], h1 = cp[pstride + ix[2]], h3 = cp[3 * pstride + ix[2]];   // :7723-7730
-        const float a0 = __fadd_rn(MUL(h0.x, h0.x), MUL(h0.y, h0.y)), a1 = __fadd_rn(MUL(h1.x, h1.x), MUL(h1.y, h1.y));
-        const float a2 = __fadd_rn(MUL(h2.x, h2.x), MUL(h2.y, h2.y)), a3 = __fadd_rn(MUL(h3.x, h3.x), MUL(h3.y, h3.y));
-        const float n02 = __fsqrt_rn(__fadd_rn(MUL(a0, a0), MUL(a2, a2))), n13 = __fsqrt_rn(__fadd_rn(MUL(a1, a1), MUL(a3, a3)));
-        const float x0r = __fdiv_rn(sum4(MUL(h0.x, y0.x), MUL(h0.y, y0.y), MUL(h2.x, y1.x), MUL(h2.y, y1.y)), n02);
-        const float x0i = __fdiv_rn(sum4(MUL(h0.x, y0.y), -MUL(h0.y, y0.x), -MUL(h2.x, y1.y), MUL(h2.y, y1.x)), n02);
-        const float x1r = __fdiv_rn(sum4(-MUL(h2.x, y0.x), -MUL(h2.y, y0.y), MUL(h0.x, y1.x), MUL(h0.y, y1.y)), n02);
-        const float x1i = __fdiv_rn(-sum4(-MUL(h2.x, y0.y), MUL(h2.y, y0.x), -MUL(h0.x, y1.y), MUL(h0.y, y1.x)), n02);
-        const float x2r = __fdiv_rn(sum4(MUL(h1.x, y2.x), MUL(h1.y, y2.y), MUL(h3.x, y3.x), MUL(h3.y, y3.y)), n13);
-        const float x2i = __fdiv_rn(sum4(MUL(h1.x, y2.y), -MUL(h1.y, y2.x), -MUL(h3.x, y3.y), MUL(h3.y, y3.x)), n13);
-        const float x3r = __fdiv_rn(sum4(-MUL(h3.x, y2.x), -MUL(h3.y, y2.y), MUL(h1.x, y3.x), MUL(h1.y, y3.y)), n13);
-        const float x3i = __fdiv_rn(-sum4(-MUL(h3.x, y2.y), MUL(h3.y, y2.x), -MUL(h1.x, y3.y), MUL(h1.y, y3.x)), n13);
-        demap_store(x0r, x0i, P.mod, P.Qm, c, o);
-        demap_store(x1r, x1i, P.mod, P.Qm, c + P.Qm, o + P.Qm);
-        demap_store(x2r, x2i, P.mod, P.Qm, c + 2 * P.Qm, o + 2 * P.Qm);
-        demap_store(x3r, x3i, P.mod, P.Qm, c + 3 * P.Qm, o + 3 * P.Qm);
+        const float2 y[4] = {gr[ix[0]], gr[ix[1]], gr[ix[2]], gr[ix[3]]};
+        float2 x[4];
+        sfbc4(y, cp[ix[0]], cp[pstride + ix[2]], cp[2 * pstride + ix[0]], cp[3 * pstride + ix[2]], x);
+        for (int t = 0; t < 4; t++) demap_store(x[t].x, x[t].y, P.mod, P.Qm, c + t * P.Qm, o + t * P.Qm);
     }
 }
 

@@ -53,6 +53,38 @@ __device__ __forceinline__ void zf_1port(float2 y, float2 h, float &xr, float &x
     xi = __fdiv_rn(__fsub_rn(__fmul_rn(y.y, h.x), __fmul_rn(y.x, h.y)), nrm);
 }
 
+// ---- transmit-diversity combining shared by PDSCH, PBCH and PDCCH (pre_decoder_and_matched_filter_dl + layer_demapper_dl,
+// liblte_phy.cc:7691-7765, 7505-7512), in the reference's operation order (IEEE adds/multiplies, no contraction)
+__device__ __forceinline__ float td_sum4(float a, float b, float c, float d) { return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d); }
+#define TD_MUL(a, b) __fmul_rn((a), (b))
+// two ports: symbols y0,y1 of one pair, both estimates taken at the EVEN element (:7696-7699)
+__device__ __forceinline__ void sfbc2(float2 y0, float2 y1, float2 h0, float2 h1, float2 &x0, float2 &x1)
+{
+    const float a0 = __fadd_rn(TD_MUL(h0.x, h0.x), TD_MUL(h0.y, h0.y)), a1 = __fadd_rn(TD_MUL(h1.x, h1.x), TD_MUL(h1.y, h1.y));
+    const float n = __fsqrt_rn(__fadd_rn(TD_MUL(a0, a0), TD_MUL(a1, a1)));                        // sic: sqrt(|h0|^4 + |h1|^4)
+    x0.x = __fdiv_rn(td_sum4(TD_MUL(h0.x, y0.x), TD_MUL(h0.y, y0.y), TD_MUL(h1.x, y1.x), TD_MUL(h1.y, y1.y)), n);
+    x0.y = __fdiv_rn(td_sum4(TD_MUL(h0.x, y0.y), -TD_MUL(h0.y, y0.x), -TD_MUL(h1.x, y1.y), TD_MUL(h1.y, y1.x)), n);
+    x1.x = __fdiv_rn(td_sum4(-TD_MUL(h1.x, y0.x), -TD_MUL(h1.y, y0.y), TD_MUL(h0.x, y1.x), TD_MUL(h0.y, y1.y)), n);
+    x1.y = __fdiv_rn(td_sum4(TD_MUL(h1.x, y0.y), -TD_MUL(h1.y, y0.x), TD_MUL(h0.x, y1.y), -TD_MUL(h0.y, y1.x)), n);
+}
+// four ports: h0,h2 at element 0 of the group, h1,h3 at element 2 (:7723-7730)
+__device__ __forceinline__ void sfbc4(const float2 y[4], float2 h0, float2 h1, float2 h2, float2 h3, float2 x[4])
+{
+    const float2 y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+    const float a0 = __fadd_rn(TD_MUL(h0.x, h0.x), TD_MUL(h0.y, h0.y)), a1 = __fadd_rn(TD_MUL(h1.x, h1.x), TD_MUL(h1.y, h1.y));
+    const float a2 = __fadd_rn(TD_MUL(h2.x, h2.x), TD_MUL(h2.y, h2.y)), a3 = __fadd_rn(TD_MUL(h3.x, h3.x), TD_MUL(h3.y, h3.y));
+    const float n02 = __fsqrt_rn(__fadd_rn(TD_MUL(a0, a0), TD_MUL(a2, a2))), n13 = __fsqrt_rn(__fadd_rn(TD_MUL(a1, a1), TD_MUL(a3, a3)));
+    x[0].x = __fdiv_rn(td_sum4(TD_MUL(h0.x, y0.x), TD_MUL(h0.y, y0.y), TD_MUL(h2.x, y1.x), TD_MUL(h2.y, y1.y)), n02);
+    x[0].y = __fdiv_rn(td_sum4(TD_MUL(h0.x, y0.y), -TD_MUL(h0.y, y0.x), -TD_MUL(h2.x, y1.y), TD_MUL(h2.y, y1.x)), n02);
+    x[1].x = __fdiv_rn(td_sum4(-TD_MUL(h2.x, y0.x), -TD_MUL(h2.y, y0.y), TD_MUL(h0.x, y1.x), TD_MUL(h0.y, y1.y)), n02);
+    x[1].y = __fdiv_rn(-td_sum4(-TD_MUL(h2.x, y0.y), TD_MUL(h2.y, y0.x), -TD_MUL(h0.x, y1.y), TD_MUL(h0.y, y1.x)), n02);
+    x[2].x = __fdiv_rn(td_sum4(TD_MUL(h1.x, y2.x), TD_MUL(h1.y, y2.y), TD_MUL(h3.x, y3.x), TD_MUL(h3.y, y3.y)), n13);
+    x[2].y = __fdiv_rn(td_sum4(TD_MUL(h1.x, y2.y), -TD_MUL(h1.y, y2.x), -TD_MUL(h3.x, y3.y), TD_MUL(h3.y, y3.x)), n13);
+    x[3].x = __fdiv_rn(td_sum4(-TD_MUL(h3.x, y2.x), -TD_MUL(h3.y, y2.y), TD_MUL(h1.x, y3.x), TD_MUL(h1.y, y3.y)), n13);
+    x[3].y = __fdiv_rn(-td_sum4(-TD_MUL(h3.x, y2.y), TD_MUL(h3.y, y2.x), -TD_MUL(h1.x, y3.y), TD_MUL(h1.y, y3.x)), n13);
+}
+
+
 // What the fused receive kernel needs to know about one allocation (device pointers into the context's cached tables).
 struct FusedAlloc {
     const int *re_idx;        // [3][idx_stride]  PDSCH resource elements per subframe class (0, 5, other)

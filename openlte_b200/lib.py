@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libopenlte_b200.so")
 
-OK, ERR_ARGS, ERR_CUDA, ERR_DECODE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+OK, ERR_ARGS, ERR_CUDA, ERR_DECODE, ERR_UNSUPPORTED, ERR_CONTENTS = 0, -1, -2, -3, -4, -5
 FS_IDX = {1.92: 0, 3.84: 1, 7.68: 2, 15.36: 3, 30.72: 4}
 MOD_BPSK, MOD_QPSK, MOD_16QAM, MOD_64QAM = 0, 1, 2, 3
 TURBO_REF_EXACT, TURBO_MAXLOGMAP = 0, 1
@@ -32,6 +32,26 @@ class Alloc(C.Structure):
         for j, (x, y) in enumerate(zip(prb, p1)):
             a.prb[0][j] = int(x); a.prb[1][j] = int(y)
         return a
+
+
+class BchResult(C.Structure):
+    """lteb200_bch_result"""
+    _fields_ = [("ok", C.c_int32), ("N_ant", C.c_int32), ("offset", C.c_int32), ("bits", C.c_uint8 * 24)]
+
+
+class PdcchRaw(C.Structure):
+    """lteb200_pdcch_raw"""
+    _fields_ = [("cfi", C.c_int32), ("N_symbs", C.c_int32), ("found", C.c_int32 * 12), ("rnti", C.c_int32 * 12), ("bits", (C.c_uint8 * 32) * 12)]
+
+
+class Dci(C.Structure):
+    """lteb200_dci"""
+    _fields_ = [("alloc", Alloc), ("mcs", C.c_int32), ("format", C.c_int32)]
+
+    def as_dict(self):
+        a = self.alloc; n = min(int(a.N_prb), 110)
+        return dict(rnti=int(a.rnti), tbs=int(a.tbs), mcs=int(self.mcs), N_prb=int(a.N_prb), rv_idx=int(a.rv_idx), mod_type=int(a.mod_type),
+                    tx_mode=int(a.tx_mode), chan_type=0, prb=[int(a.prb[0][j]) for j in range(n)], prb1=[int(a.prb[1][j]) for j in range(n)])
 
 
 # name -> (restype, argtypes); every symbol declared in include/lte_b200.h
@@ -58,6 +78,11 @@ SYMBOLS = {
     "lteb200_find_coarse_timing_and_freq_offset": (_i, [_vp, _vp, _vp, _ll, _i, _u32, _vp, _vp, _vp]),
     "lteb200_find_pss_and_fine_timing": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lteb200_find_sss": (_i, [_vp, _vp, _vp, _ll, _i, _i, _u32, _vp, _f, _vp, _vp]),
+    "lteb200_bch_decode_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "lteb200_bch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _vp, _vp, _vp, _vp]),
+    "lteb200_pdcch_decode_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp]),
+    "lteb200_pdcch_unpack": (_i, [_vp, _i, _i, _vp, _vp]),
+    "lteb200_pdcch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _u32, C.c_uint8, _f, _i, _vp, _vp, _vp, _vp]),
     "lteb200_freq_shift_batch": (_i, [_vp, _vp, _i, _ll, _ll, _f, _i, _vp, _vp]),
     "lteb200_freq_shift": (_i, [_vp, _vp, _vp, _u32, _u32, _f, _i]),
     "lteb200_set_freq_offset": (_i, [_vp, _f, _ll]),

@@ -172,3 +172,67 @@ def pdsch_decode_nant(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, N_ant, sub
     rc = lib().op_pdsch_decode_nant(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), N_rb_dl, N_id_cell, N_ant, subfr, cfi, mod, int(prb.size), _p(prb), tbs, rv,
                                     rnti, turbo_mode, n_iter, _p(out), _p(soft), C.byref(n))
     return rc, out[:tbs], soft[:n.value]
+
+
+# ---- control channels (oracle/port/control.cc)
+def _alloc_dict(o):
+    n = int(o[3])
+    return dict(rnti=int(o[0]), tbs=int(o[1]), mcs=int(o[2]), N_prb=n, rv_idx=int(o[4]), mod_type=int(o[5]), tx_mode=int(o[6]),
+                chan_type=int(o[7]), prb=[int(x) for x in o[8:8 + min(n, 110)]], prb1=[int(x) for x in o[118:118 + min(n, 110)]])
+
+
+def tbs_1a(i_tbs, n_prb_1a):
+    return lib().op_tbs_1a(i_tbs, n_prb_1a)
+
+
+def tbs_1c(i):
+    return lib().op_tbs_1c(i)
+
+
+def rate_unmatch_conv(e, N_c):
+    e = np.ascontiguousarray(e, np.float32); d = np.zeros(3 * N_c, np.float32)
+    lib().op_rate_unmatch_conv(_p(e), int(e.size), N_c, _p(d))
+    return d
+
+
+def viterbi_decode(d):
+    d = np.ascontiguousarray(d, np.float32); c = np.zeros(d.size + 80, np.uint8)
+    n = lib().op_viterbi_decode(_p(d), int(d.size), _p(c))
+    return c[:n].copy()
+
+
+def bch_channel_decode(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell):
+    """ce_*: [4][16][1200].  Returns (err, N_ant, bits24, offset)."""
+    rx_re, rx_im, ce_re, ce_im = [np.ascontiguousarray(a, np.float32) for a in (rx_re, rx_im, ce_re, ce_im)]
+    na = C.c_int(0); off = C.c_int(0); out = np.zeros(24, np.uint8)
+    err = lib().op_bch_channel_decode(_p(rx_re), _p(rx_im), _p(ce_re), _p(ce_im), N_rb_dl, N_id_cell, C.byref(na), _p(out), C.byref(off))
+    return err, na.value, out, off.value
+
+
+def pdcch_cce_map(N_rb_dl, N_id_cell, N_ant, N_symbs, phich_res=1.0):
+    re_of = np.zeros((N_symbs * N_rb_dl * 3 // 9 + 1) * 36, np.int32); nreg = C.c_int(0)
+    n = lib().op_pdcch_cce_map(N_rb_dl, N_id_cell, N_ant, N_symbs, C.c_float(phich_res), _p(re_of), C.byref(nreg))
+    return re_of[:n * 36].reshape(n, 36).copy(), nreg.value
+
+
+def dci_1a_unpack(bits, rnti, N_rb_dl, N_ant):
+    b = np.ascontiguousarray(bits, np.uint8); o = np.zeros(228, np.int32)
+    err = lib().op_dci_1a_unpack(_p(b), rnti, N_rb_dl, N_ant, _p(o))
+    return err, _alloc_dict(o)
+
+
+def dci_1c_unpack(bits, rnti, N_rb_dl, N_ant):
+    b = np.ascontiguousarray(bits, np.uint8); o = np.zeros(228, np.int32)
+    err = lib().op_dci_1c_unpack(_p(b), rnti, N_rb_dl, N_ant, _p(o))
+    return err, _alloc_dict(o)
+
+
+def pdcch_channel_decode(rx_re, rx_im, ce_re, ce_im, N_rb_dl, N_id_cell, N_ant, subfr, phich_res=1.0):
+    """Returns dict(err, cfi, N_symbs, allocs, raw_found[12], raw_rnti[12], raw_bits[12][32])."""
+    rx_re, rx_im, ce_re, ce_im = [np.ascontiguousarray(a, np.float32) for a in (rx_re, rx_im, ce_re, ce_im)]
+    cfi = C.c_int(0); ns = C.c_int(0); na = C.c_int(0); al = np.zeros((6, 228), np.int32)
+    rf = np.zeros(12, np.int32); rr = np.zeros(12, np.int32); rb = np.zeros((12, 32), np.uint8)
+    err = lib().op_pdcch_channel_decode(_p(rx_re), _p(rx_im), _p(ce_re), _p(ce_im), N_rb_dl, N_id_cell, N_ant, subfr, C.c_float(phich_res),
+                                        C.byref(cfi), C.byref(ns), C.byref(na), _p(al), _p(rf), _p(rr), _p(rb))
+    return dict(err=err, cfi=cfi.value, N_symbs=ns.value, allocs=[_alloc_dict(al[a]) for a in range(na.value)], raw_found=rf, raw_rnti=rr,
+                raw_bits=rb)

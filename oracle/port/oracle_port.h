@@ -81,6 +81,23 @@ int op_find_pss(const float *i_samps, const float *q_samps, int fs_idx, int N_rb
 int op_find_sss(const float *i_samps, const float *q_samps, int fs_idx, int N_rb_dl, uint32_t N_id_2, uint32_t *symb_starts,
                 float pss_thresh, uint32_t *N_id_1, uint32_t *frame_start_idx);
 
+/* control channels (control.cc) */
+int  op_tbs_1a(int i_tbs, int n_prb_1a);
+int  op_tbs_1c(int i);
+int  op_rate_unmatch_conv(const float *e, int E, int N_c, float *d);
+int  op_viterbi_decode(const float *d, int N_d, uint8_t *c);
+int  op_bch_decode_bits(const float *in1920, int N_ant, uint8_t *out24);
+int  op_bch_channel_decode(const float *rx_re, const float *rx_im, const float *ce_re, const float *ce_im, int N_rb_dl, int N_id_cell,
+                           int *N_ant, uint8_t *out24, int *offset);
+int  op_dci_sizes(int N_rb_dl, int *size_1a, int *size_1c);
+void op_control_reg_positions(int N_rb_dl, int N_id_cell, float phich_res, int *pcfich_k, int *phich_k, int *N_reg_phich);
+int  op_pdcch_cce_map(int N_rb_dl, int N_id_cell, int N_ant, int N_symbs, float phich_res, int *re_of, int *N_reg_out);
+int  op_dci_decode_bits(const float *soft, int E, int n_dci, uint8_t *dci_bits, int *rnti);
+int  op_dci_1a_unpack(const uint8_t *bits, int rnti, int N_rb_dl, int N_ant, int *alloc228);
+int  op_dci_1c_unpack(const uint8_t *bits, int rnti, int N_rb_dl, int N_ant, int *alloc228);
+int  op_pdcch_channel_decode(const float *rx_re, const float *rx_im, const float *ce_re, const float *ce_im, int N_rb_dl, int N_id_cell,
+                             int N_ant, int subfr, float phich_res, int *cfi, int *N_symbs, int *N_alloc, int *allocs, int *raw_found,
+                             int *raw_rnti, uint8_t *raw_bits);
 #ifdef __cplusplus
 }
 #endif

@@ -233,6 +233,31 @@ class RefPhy:
         err = lib().ref_bch_channel_decode(self.h, sf.h, N_id_cell, C.byref(na), _p(out), C.byref(n), C.byref(off))
         return err, na.value, out[:n.value], off.value
 
+    def bch_encode(self, sf, bits, N_id_cell, N_ant, sfn):
+        b = _u8(bits)
+        return lib().ref_bch_channel_encode(self.h, sf.h, _p(b), int(b.size), N_id_cell, N_ant, C.c_uint(sfn))
+
+    def pdcch_encode(self, sf, N_id_cell, N_ant, cfi, allocs, phich_res=1.0, phich_dur=0):
+        """allocs: list of dict(rnti, mcs, rv_idx, N_prb, prb0) -- DCI 1A in the common search space, aggregation level 4"""
+        a = np.array([[x["rnti"], x["mcs"], x.get("rv_idx", 0), x["N_prb"], x["prb0"]] for x in allocs], np.int32).reshape(-1, 5)
+        return lib().ref_pdcch_channel_encode(self.h, sf.h, N_id_cell, N_ant, C.c_float(phich_res), phich_dur, cfi, len(allocs), _p(a))
+
+    def pdcch_decode2(self, sf, N_id_cell, N_ant, phich_res=1.0, phich_dur=0):
+        cfi = C.c_int(0); ns = C.c_int(0); na = C.c_int(0); out = np.zeros((6, 228), np.int32)
+        err = lib().ref_pdcch_channel_decode2(self.h, sf.h, N_id_cell, N_ant, C.c_float(phich_res), phich_dur, C.byref(cfi), C.byref(ns),
+                                              C.byref(na), _p(out))
+        return err, cfi.value, ns.value, [_alloc_dict(out[a]) for a in range(na.value)]
+
+    def rate_unmatch_conv(self, e_bits, N_c):
+        e = _f32(e_bits); d = np.zeros(3 * N_c + 8, np.float32); n = C.c_int(0)
+        lib().ref_rate_unmatch_conv(self.h, _p(e), int(e.size), N_c, _p(d), C.byref(n))
+        return d[:n.value].copy()
+
+    def viterbi_decode(self, d_bits):
+        d = _f32(d_bits); c = np.zeros(d.size + 80, np.uint8); n = C.c_int(0)
+        lib().ref_viterbi_decode(self.h, _p(d), int(d.size), _p(c), C.byref(n))
+        return c[:n.value].copy()
+
     def pdcch_decode(self, sf, N_id_cell, N_ant, phich_res=1.0, phich_dur=0):
         cfi = C.c_int(0); na = C.c_int(0); out = np.zeros((6, 118), np.int32)
         err = lib().ref_pdcch_channel_decode(self.h, sf.h, N_id_cell, N_ant, C.c_float(phich_res), phich_dur, C.byref(cfi), C.byref(na), _p(out))
@@ -280,3 +305,29 @@ def pre_decoder(y_re, y_im, h_re, h_im, N_ant=1):
     x_re = np.zeros(M + 8, np.float32); x_im = np.zeros(M + 8, np.float32)
     ml = lib().ref_pre_decoder_dl(_p(y_re), _p(y_im), _p(h_re), _p(h_im), h_len, M, N_ant, _p(x_re), _p(x_im))
     return x_re[:M], x_im[:M], ml
+
+
+def _alloc_dict(o):
+    n = int(o[3])
+    return dict(rnti=int(o[0]), tbs=int(o[1]), mcs=int(o[2]), N_prb=n, rv_idx=int(o[4]), mod_type=int(o[5]), tx_mode=int(o[6]),
+                chan_type=int(o[7]), prb=[int(x) for x in o[8:8 + n]], prb1=[int(x) for x in o[118:118 + n]])
+
+
+def dci_1a_unpack(bits, rnti, N_rb_dl, N_ant):
+    b = _u8(bits); o = np.zeros(228, np.int32)
+    err = lib().ref_dci_1a_unpack(_p(b), int(b.size), rnti, N_rb_dl, N_ant, _p(o))
+    return err, _alloc_dict(o)
+
+
+def dci_1c_unpack(bits, rnti, N_rb_dl, N_ant):
+    b = _u8(bits); o = np.zeros(228, np.int32)
+    err = lib().ref_dci_1c_unpack(_p(b), int(b.size), rnti, N_rb_dl, N_ant, _p(o))
+    return err, _alloc_dict(o)
+
+
+def tbs_71721(i_tbs, n_prb):
+    return lib().ref_tbs_71721(i_tbs, n_prb)
+
+
+def tbs_71723(i):
+    return lib().ref_tbs_71723(i)

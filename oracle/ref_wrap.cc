@@ -42,6 +42,14 @@ void dlsch_channel_encode(LIBLTE_PHY_STRUCT *, uint8 *, uint32, uint32, uint32, 
                           uint32, uint32, uint32, uint8 *, uint32 *);                                    /* :12664 */
 void viterbi_decode_siso(LIBLTE_PHY_STRUCT *, int8 *, uint32, uint32, uint32, uint32 *, int8 *, uint32 *); /* :10341 */
 
+void rate_unmatch_conv(LIBLTE_PHY_STRUCT *, float *, uint32, uint32, float *, uint32 *);                  /* :1625 */
+void viterbi_decode(LIBLTE_PHY_STRUCT *, float *, uint32, uint32, uint32, uint32 *, uint8 *, uint32 *);     /* :1445 */
+LIBLTE_ERROR_ENUM dci_1a_unpack(uint8 *, uint32, LIBLTE_PHY_DCI_CA_PRESENCE_ENUM, uint16, uint32, uint8,
+                                LIBLTE_PHY_ALLOCATION_STRUCT *);                                           /* :2021 */
+LIBLTE_ERROR_ENUM dci_1c_unpack(uint8 *, uint32, uint16, uint32, uint8, LIBLTE_PHY_ALLOCATION_STRUCT *);    /* :2061 */
+extern uint32 TBS_71721[27][110];                                                                          /* :477 */
+extern uint32 TBS_71723[32];                                                                               /* :749 */
+
 extern "C" {
 
 /* ------------------------------------------------------------------ context */
@@ -390,5 +398,84 @@ int ref_pdcch_channel_decode(void *h, void *subframe, int N_id_cell, int N_ant, 
     }
     return err;
 }
+
+/* transmit side of the control channels, used to build fixtures */
+int ref_bch_channel_encode(void *h, void *subframe, const uint8 *bits, int N_bits, int N_id_cell, int N_ant, unsigned sfn)
+{
+    return (int)liblte_phy_bch_channel_encode((LIBLTE_PHY_STRUCT *)h, (uint8 *)bits, N_bits, N_id_cell, (uint8)N_ant,
+                                              (LIBLTE_PHY_SUBFRAME_STRUCT *)subframe, sfn);
+}
+/* alloc_in: per allocation {rnti, mcs, rv_idx, N_prb, first prb}; DCI 1A, localized, aggregation level 4 (all the reference can send) */
+int ref_pdcch_channel_encode(void *h, void *subframe, int N_id_cell, int N_ant, float phich_res, int phich_dur, int cfi, int n_alloc,
+                             const int *alloc_in)
+{
+    static LIBLTE_PHY_PCFICH_STRUCT pcfich;
+    static LIBLTE_PHY_PHICH_STRUCT  phich;
+    static LIBLTE_PHY_PDCCH_STRUCT  pdcch;
+    memset(&pcfich, 0, sizeof(pcfich)); memset(&phich, 0, sizeof(phich)); memset(&pdcch, 0, sizeof(pdcch));
+    pcfich.cfi = cfi;
+    pdcch.N_alloc = n_alloc;
+    for (int a = 0; a < n_alloc; a++) {
+        const int *in = alloc_in + 5 * a;
+        LIBLTE_PHY_ALLOCATION_STRUCT *al = &pdcch.alloc[a];
+        al->chan_type = LIBLTE_PHY_CHAN_TYPE_DLSCH; al->rnti = (uint16)in[0]; al->mcs = (uint8)in[1]; al->rv_idx = in[2]; al->N_prb = in[3];
+        for (int j = 0; j < in[3]; j++) { al->prb[0][j] = in[4] + j; al->prb[1][j] = in[4] + j; }
+        al->pre_coder_type = LIBLTE_PHY_PRE_CODER_TYPE_TX_DIVERSITY; al->mod_type = LIBLTE_PHY_MODULATION_TYPE_QPSK;
+        al->N_codewords = 1; al->tx_mode = N_ant == 1 ? 1 : 2;
+    }
+    return (int)liblte_phy_pdcch_channel_encode((LIBLTE_PHY_STRUCT *)h, &pcfich, &phich, &pdcch, N_id_cell, (uint8)N_ant, phich_res,
+                                                (LIBLTE_RRC_PHICH_DURATION_ENUM)phich_dur, (LIBLTE_PHY_SUBFRAME_STRUCT *)subframe);
+}
+/* decode, full detail: per alloc {rnti, tbs, mcs, N_prb, rv_idx, mod_type, tx_mode, chan_type, prb[0][0..110), prb[1][0..110)}; also the PCFICH CFI */
+int ref_pdcch_channel_decode2(void *h, void *subframe, int N_id_cell, int N_ant, float phich_res, int phich_dur, int *cfi, int *N_symbs,
+                              int *N_alloc, int *alloc_out /* [6][8+220] */)
+{
+    static LIBLTE_PHY_PCFICH_STRUCT pcfich;
+    static LIBLTE_PHY_PHICH_STRUCT  phich;
+    static LIBLTE_PHY_PDCCH_STRUCT  pdcch;
+    memset(&pcfich, 0, sizeof(pcfich)); memset(&phich, 0, sizeof(phich)); memset(&pdcch, 0, sizeof(pdcch));
+    int err = (int)liblte_phy_pdcch_channel_decode((LIBLTE_PHY_STRUCT *)h, (LIBLTE_PHY_SUBFRAME_STRUCT *)subframe, N_id_cell,
+                                                   (uint8)N_ant, phich_res, (LIBLTE_RRC_PHICH_DURATION_ENUM)phich_dur,
+                                                   &pcfich, &phich, &pdcch);
+    *cfi = (int)pcfich.cfi; *N_symbs = (int)pdcch.N_symbs; *N_alloc = (int)pdcch.N_alloc;
+    for (uint32 a = 0; a < pdcch.N_alloc && a < 6; a++) {
+        int *o = alloc_out + a * (8 + 220);
+        o[0] = pdcch.alloc[a].rnti; o[1] = pdcch.alloc[a].tbs; o[2] = pdcch.alloc[a].mcs; o[3] = pdcch.alloc[a].N_prb;
+        o[4] = pdcch.alloc[a].rv_idx; o[5] = pdcch.alloc[a].mod_type; o[6] = pdcch.alloc[a].tx_mode; o[7] = pdcch.alloc[a].chan_type;
+        for (uint32 j = 0; j < pdcch.alloc[a].N_prb && j < 110; j++) { o[8 + j] = pdcch.alloc[a].prb[0][j]; o[8 + 110 + j] = pdcch.alloc[a].prb[1][j]; }
+    }
+    return err;
+}
+/* pieces, for checking the restatement function by function */
+void ref_rate_unmatch_conv(void *h, const float *e_bits, int N_e, int N_c, float *d_bits, int *N_d)
+{
+    uint32 n = 0;
+    rate_unmatch_conv((LIBLTE_PHY_STRUCT *)h, (float *)e_bits, N_e, N_c, d_bits, &n);
+    *N_d = (int)n;
+}
+void ref_viterbi_decode(void *h, const float *d_bits, int N_d, uint8 *c_bits, int *N_c)
+{
+    uint32 g[3] = {0133, 0171, 0165}, n = 0;
+    viterbi_decode((LIBLTE_PHY_STRUCT *)h, (float *)d_bits, N_d, 7, 3, g, c_bits, &n);
+    *N_c = (int)n;
+}
+int ref_dci_1a_unpack(const uint8 *bits, int N_bits, int rnti, int N_rb_dl, int N_ant, int *o /*[8+220]*/)
+{
+    static LIBLTE_PHY_ALLOCATION_STRUCT al; memset(&al, 0, sizeof(al));
+    int err = (int)dci_1a_unpack((uint8 *)bits, N_bits, LIBLTE_PHY_DCI_CA_NOT_PRESENT, (uint16)rnti, N_rb_dl, (uint8)N_ant, &al);
+    o[0] = al.rnti; o[1] = al.tbs; o[2] = al.mcs; o[3] = al.N_prb; o[4] = al.rv_idx; o[5] = al.mod_type; o[6] = al.tx_mode; o[7] = al.chan_type;
+    for (uint32 j = 0; j < al.N_prb && j < 110; j++) { o[8 + j] = al.prb[0][j]; o[8 + 110 + j] = al.prb[1][j]; }
+    return err;
+}
+int ref_dci_1c_unpack(const uint8 *bits, int N_bits, int rnti, int N_rb_dl, int N_ant, int *o /*[8+220]*/)
+{
+    static LIBLTE_PHY_ALLOCATION_STRUCT al; memset(&al, 0, sizeof(al));
+    int err = (int)dci_1c_unpack((uint8 *)bits, N_bits, (uint16)rnti, N_rb_dl, (uint8)N_ant, &al);
+    o[0] = al.rnti; o[1] = al.tbs; o[2] = al.mcs; o[3] = al.N_prb; o[4] = al.rv_idx; o[5] = al.mod_type; o[6] = al.tx_mode; o[7] = al.chan_type;
+    for (uint32 j = 0; j < al.N_prb && j < 110; j++) { o[8 + j] = al.prb[0][j]; o[8 + 110 + j] = al.prb[1][j]; }
+    return err;
+}
+int ref_tbs_71721(int i_tbs, int n_prb) { return (int)TBS_71721[i_tbs][n_prb - 1]; }
+int ref_tbs_71723(int i) { return (int)TBS_71723[i]; }
 
 } /* extern "C" */

@@ -38,6 +38,21 @@ int main(int argc, char **argv)
     const uint32 fs0 = frame_start_idx - phy->N_samps_per_frame;
     static LIBLTE_PHY_SUBFRAME_STRUCT subframe;
     if (liblte_phy_get_dl_subframe_and_ce(phy, i_buf.data(), q_buf.data(), fs0, (uint8)atoi(argv[4]), N_id_cell, 1, &subframe) != LIBLTE_SUCCESS) { printf("CE_FAILED\n"); return 1; }
+    // PCFICH + PDCCH: the scan takes the allocation from here (LTE_fdd_dl_fs_samp_buf.cc:453, 499)
+    static LIBLTE_PHY_PCFICH_STRUCT pcfich; static LIBLTE_PHY_PHICH_STRUCT phich; static LIBLTE_PHY_PDCCH_STRUCT pdcch;
+    LIBLTE_ERROR_ENUM pe = liblte_phy_pdcch_channel_decode(phy, &subframe, N_id_cell, 1, 1.0f, LIBLTE_RRC_PHICH_DURATION_NORMAL, &pcfich, &phich, &pdcch);
+    printf("pdcch err=%d cfi=%u N_symbs=%u N_alloc=%u", (int)pe, pcfich.cfi, pdcch.N_symbs, pdcch.N_alloc);
+    if (pdcch.N_alloc > 0) printf(" rnti=0x%04X tbs=%u N_prb=%u prb0=%u mod=%d rv=%u", pdcch.alloc[0].rnti, pdcch.alloc[0].tbs, pdcch.alloc[0].N_prb,
+                                  pdcch.alloc[0].prb[0][0], (int)pdcch.alloc[0].mod_type, pdcch.alloc[0].rv_idx);
+    putchar('\n');
+    if (pe == LIBLTE_SUCCESS && pdcch.N_alloc > 0) {
+        static uint8 sib_bits[LIBLTE_MAX_MSG_SIZE];
+        uint32 n_sib = 0;
+        LIBLTE_ERROR_ENUM se = liblte_phy_pdsch_channel_decode(phy, &subframe, &pdcch.alloc[0], pdcch.N_symbs, N_id_cell, 1, sib_bits, &n_sib);
+        printf("pdsch_from_dci err=%d N_bits=%u bits=", (int)se, n_sib);
+        for (uint32 k = 0; k < n_sib; k++) putchar('0' + sib_bits[k]);
+        putchar('\n');
+    }
     static LIBLTE_PHY_ALLOCATION_STRUCT alloc;
     memset(&alloc, 0, sizeof(alloc));
     alloc.rnti = (uint16)strtol(argv[5], NULL, 0); alloc.tbs = atoi(argv[6]); alloc.N_prb = atoi(argv[7]);

@@ -37,4 +37,7 @@ def test_scan_on_reference_capture(tmp_path):
     assert "sss N_id_1=0 frame_start_idx=307185 N_id_cell=0" in out, out
     bits = "".join(map(str, z["sib1_bits"]))
     assert f"pdsch err=0 N_bits=144 bits={bits}" in out, out
+    # the allocation found by the PDCCH decode is the one the reference finds, and decoding with it gives the same SIB1
+    assert f"pdcch err=0 cfi={int(z['cfi'])} N_symbs={int(z['cfi'])}" in out and f"rnti=0xFFFF tbs=144 N_prb=4 prb0=0 mod=1 rv={int(z['rv'])}" in out, out
+    assert f"pdsch_from_dci err=0 N_bits=144 bits={bits}" in out, out
     assert "null_check=1" in out            # LIBLTE_ERROR_INVALID_INPUTS

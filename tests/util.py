@@ -30,8 +30,10 @@ def stream_ptr():
 # Synthetic downlink signal through the REFERENCE's own transmit functions: CRS +
 # PDSCH allocations -> IFFT, followed by a CRS-only subframe (the estimator reads symbols 14-15).
 def ref_loopback(refo, subfr, allocs, N_id_cell=0, cfi=2, N_rb_dl=100, fs=30.72, seed=0, gain=1.0 + 0j, noise=0.0,
-                 frame_start=0, n_extra=1, N_ant=1, ant_gains=None):
-    """allocs: list of dict(mod, prb, tbs, rnti).  Returns dict with i/q sample arrays (float32), tb bits, phy handle."""
+                 frame_start=0, n_extra=1, N_ant=1, ant_gains=None, bch=None, pdcch=None):
+    """allocs: list of dict(mod, prb, tbs, rnti).  bch: dict(bits[24], sfn) -> PBCH in the first subframe (use subfr=0);
+    pdcch: dict(cfi, allocs=[dict(rnti, mcs, N_prb, prb0)]) -> PCFICH + DCI 1A in the first subframe.
+    Returns dict with i/q sample arrays (float32), tb bits, phy handle."""
     rng = np.random.default_rng(seed)
     phy = refo.RefPhy(fs=fs, N_id_cell=N_id_cell, N_ant=N_ant, N_rb_dl=N_rb_dl)
     if ant_gains is None:
@@ -48,6 +50,10 @@ def ref_loopback(refo, subfr, allocs, N_id_cell=0, cfi=2, N_rb_dl=100, fs=30.72,
                 tb = rng.integers(0, 2, a["tbs"]).astype(np.uint8)
                 tbs_bits.append(tb)
                 phy.pdsch_encode(sf, cfi, N_id_cell, N_ant, a["mod"], a["prb"], a["tbs"], a["rnti"], tb, rv=a.get("rv", 0))
+            if bch is not None:
+                assert phy.bch_encode(sf, bch["bits"], N_id_cell, N_ant, bch["sfn"]) == 0
+            if pdcch is not None:
+                assert phy.pdcch_encode(sf, N_id_cell, N_ant, pdcch["cfi"], pdcch["allocs"], phich_res=pdcch.get("phich_res", 1.0)) == 0
         o = frame_start + (subfr + k) * n_sf
         for ant in range(N_ant):          # flat per-antenna channel, signals add at the receiver
             i_sf, q_sf = phy.create_dl_subframe(sf, ant, n_sf)
