@@ -48,7 +48,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 // grid: [n_sf][16][nsc] float2.  blockIdx.x = subframe * 16 + symbol.
 // WINDOWS == false: blockIdx.x = subframe*16 + symbol, start_idx[subframe] is the subframe start.
 // WINDOWS == true : blockIdx.x = window, start_idx[window] is the first sample of the N-sample DFT window; output row = window.
-template <typename T, bool WINDOWS>
+template <typename T, bool WINDOWS, bool CFO = false>
 __global__ void __launch_bounds__(512)
 ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
                   const float2 *__restrict__ tw /*[N] e^{-2 pi i k/N}*/, float2 *__restrict__ grid)
@@ -64,7 +64,7 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
     for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
         const long long s = idx + i;
         float2 v = (s >= 0 && s < n_samps) ? load_iq<T>(iq, s) : make_float2(0.f, 0.f);
-        if (P.cfo_hz != 0.f) v = cfo_rotate(v, P.cfo_base + s, P.cfo_hz, P.cfo_fs);
+        if (CFO) v = cfo_rotate(v, P.cfo_base + s, P.cfo_hz, P.cfo_fs);
         bufA[i] = v;
     }
     __syncthreads();
@@ -166,7 +166,7 @@ template <> struct Dft<16> {
 // One Stockham pass of radix R over a transform of current length n and stride s (n * s == N); thread `tid` handles
 // butterflies tid, tid + NTHR, ...  SRC_GLOBAL: inputs come from the sample stream (first pass); DST_GRID: outputs go
 // to the resource grid through the bin -> subcarrier map (last pass, where p == 0 and no twiddle applies).
-template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID>
+template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID, bool CFO = false>
 __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long long w0, long long n_samps, const float2 *__restrict__ src,
                                               float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid,
                                               float cfo_hz = 0.f, double cfo_fs = 1.0, long long cfo_base = 0)
@@ -183,7 +183,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
             if (SRC_GLOBAL) {
                 const long long sidx = w0 + i;
                 x[k] = (sidx >= 0 && sidx < n_samps) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
-                if (cfo_hz != 0.f) x[k] = cfo_rotate(x[k], cfo_base + sidx, cfo_hz, cfo_fs);
+                if (CFO) x[k] = cfo_rotate(x[k], cfo_base + sidx, cfo_hz, cfo_fs);
             } else x[k] = src[i];
         }
         Dft<R>::run(x);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
     }
 }
 
-template <int N, typename T>
+template <int N, typename T, bool CFO>
 __global__ void __launch_bounds__(N / 16 < 32 ? 32 : N / 16)
 ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
                       const float2 *__restrict__ tw, float2 *__restrict__ grid)
@@ -215,29 +215,29 @@ ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long lo
     float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
     const bool act = tid < N / 16;
     if constexpr (N == 2048) {          // 16 x 16 x 8
-        if (act) stockham_pass<N, 16, 2048, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 2048, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 128, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 1024) {   // 16 x 16 x 4
-        if (act) stockham_pass<N, 16, 1024, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 1024, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 64, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 512) {    // 16 x 8 x 4
-        if (act) stockham_pass<N, 16, 512, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 512, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 8, 32, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 256) {    // 16 x 16
-        if (act) stockham_pass<N, 16, 256, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 256, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 16, 16, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     } else {                  // 128 = 16 x 8
-        if (act) stockham_pass<N, 16, 128, T, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 128, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     }
@@ -249,11 +249,16 @@ static void launch_r16(const T *iq, long long n_samps, const long long *d_start,
 {
     const int blocks = n_sf * 16;
     switch (P.N) {
-    case 2048: ofdm_demod_r16_kernel<2048, T><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
-    case 1024: ofdm_demod_r16_kernel<1024, T><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
-    case 512:  ofdm_demod_r16_kernel<512, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
-    case 256:  ofdm_demod_r16_kernel<256, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
-    default:   ofdm_demod_r16_kernel<128, T><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break;
+    case 2048: { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<2048, T, true><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+                 else ofdm_demod_r16_kernel<2048, T, false><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
+    case 1024: { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<1024, T, true><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+                 else ofdm_demod_r16_kernel<1024, T, false><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
+    case 512:  { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<512, T, true><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+                 else ofdm_demod_r16_kernel<512, T, false><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
+    case 256:  { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<256, T, true><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+                 else ofdm_demod_r16_kernel<256, T, false><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
+    default:   { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<128, T, true><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+                 else ofdm_demod_r16_kernel<128, T, false><<<blocks, 32, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
     }
 }
 
@@ -310,10 +315,12 @@ int ofdm_demod_launch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long 
     const int threads = P.N / 4 < 64 ? 64 : (P.N / 4 > 512 ? 512 : P.N / 4);
     const size_t smem = sizeof(float2) * 2 * P.N;
     if (iq_fmt == LTEB200_IQ_F32) {
-        if (radix4) ofdm_demod_kernel<float2, false><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        if (radix4 && P.cfo_hz != 0.f) ofdm_demod_kernel<float2, false, true><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        else if (radix4) ofdm_demod_kernel<float2, false><<<n_sf * 16, threads, smem, stream>>>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
         else launch_r16<float2>((const float2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid, n_sf, stream);
     } else if (iq_fmt == LTEB200_IQ_I8) {
-        if (radix4) ofdm_demod_kernel<char2, false><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        if (radix4 && P.cfo_hz != 0.f) ofdm_demod_kernel<char2, false, true><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
+        else if (radix4) ofdm_demod_kernel<char2, false><<<n_sf * 16, threads, smem, stream>>>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid);
         else launch_r16<char2>((const char2 *)d_iq, n_samps, d_start_idx, P, tw, (float2 *)d_grid, n_sf, stream);
     } else { lteb200_set_error(ctx, "unknown I/Q format %d", iq_fmt); return LTEB200_ERR_ARGS; }
     ctx->launches += 1;
