@@ -298,3 +298,31 @@ def test_front_end_freq_shift(ctx, port):
     rx_re, rx_im, _, _ = port.get_dl_subframe_and_ce(wi, wq, fs_idx, n_rb, int(case["frame_start"]), int(case["subfr"]), cell, 1)
     want_g = (rx_re + 1j * rx_im)[:, :12 * n_rb]
     assert np.abs(g_got - want_g).max() <= 2e-6 * np.abs(want_g).max()
+
+
+def test_north_star_load_punctured_blocks(ctx):
+    """SURVEY 8d "north-star load": 12 transport blocks of K = 6144 in one 20 MHz subframe (8 PRB, 64QAM each: 6,624 coded bits
+    for an 18,444-bit mother code word, rate 0.93).  The reference's decoder cannot decode punctured code words (SURVEY H11);
+    the max-log-MAP decoder must recover every block, the reference-exact decoder must fail its CRC the way the reference does."""
+    import torch
+    from openlte_b200 import synth
+    cell, cfi, n_sf = 9, 2, 3
+    allocs = [dict(mod=3, prb=list(range(8 * a, 8 * a + 8)), tbs=6120, rnti=0x200 + a) for a in range(12)]
+    tx = synth.make_subframes(n_sf, allocs, N_id_cell=cell, seed=5, first_subfr=1)
+    stream = np.concatenate([tx["samples"].reshape(-1), synth.crs_only_tail(100, cell, int((tx["subfr_nums"][-1] + 1) % 10), 4)])
+    iq = np.stack([stream.real, stream.imag], -1).astype(np.float32)
+    d_iq = torch.from_numpy(iq).cuda()
+    start = (np.arange(n_sf) * 30720).astype(np.int64); sn = tx["subfr_nums"].astype(np.int32)
+    ca = (Alloc * 12)(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = {}
+    for mode in (1, 0):
+        tb = torch.zeros((n_sf, 12, 6120), dtype=torch.uint8, device="cuda"); ok = torch.zeros((n_sf, 12), dtype=torch.int32, device="cuda")
+        ctx.check(ctx.lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), n_sf, cfi, ca, 12, mode, 8, dptr(tb), 6120,
+                                           dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        out[mode] = (tb.cpu().numpy(), ok.cpu().numpy())
+    assert out[1][1].all(), "max-log-MAP: CRC failures on the rate-0.93 blocks"
+    for a in range(12):
+        assert np.array_equal(out[1][0][:, a], tx["tb"][a])
+    assert not out[0][1].any(), "the reference-exact decoder is expected to fail on punctured code words, as the reference does"

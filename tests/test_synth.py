@@ -17,7 +17,7 @@ def test_pieces_against_port(port):
     d = synth.turbo_encode(c)
     for i in range(2):
         assert np.array_equal(d[i].reshape(-1), port.turbo_encode(c[i]))
-    for K, E, rv in ((6144, 20700, 0), (1024, 3000, 2), (40, 200, 3)):
+    for K, E, rv in ((6144, 20700, 0), (1024, 3000, 2), (40, 200, 3), (6144, 6624, 0), (512, 700, 1)):     # the last two puncture
         D = K + 4
         dd = rng.integers(0, 2, 3 * D).astype(np.uint8)
         assert np.array_equal(dd[synth.rate_match_map(D, E, rv)], port.rate_match_turbo(dd, E, rv=rv))

@@ -41,9 +41,13 @@ def main():
     L = openlte_b200.load(); ctx = L.new_ctx(0)
     cell, cfi = 42, 2
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    for bw, (n_rb, fs_idx) in BW.items():
-        for mname, mod in MODS.items():
-            K, groups = plan(n_rb, mod, cell, cfi)
+    configs = [(bw, n_rb, fs_idx, mname, mod, None) for bw, (n_rb, fs_idx) in BW.items() for mname, mod in MODS.items()]
+    # SURVEY 8d "north-star load": 12 x K=6144 per 20 MHz subframe (8 PRB each, code rate 0.93): punctured code words, which the
+    # reference's decoder cannot decode -- GPU only, max-log-MAP is the decoder that applies
+    configs.append(("20", 100, 4, "64QAM north-star load (rate 0.93; reference cannot decode this format)", 3, (6144, [list(range(8 * a, 8 * a + 8)) for a in range(12)])))
+    for bw, n_rb, fs_idx, mname, mod, forced in configs:
+        if True:
+            K, groups = forced if forced else plan(n_rb, mod, cell, cfi)
             allocs = [dict(mod=mod, prb=g, tbs=K - 24, rnti=0x300 + i) for i, g in enumerate(groups)]
             seg = 20
             tx = synth.make_subframes(seg, allocs, N_id_cell=cell, N_rb_dl=n_rb, fs_idx=fs_idx, cfi=cfi, seed=7, first_subfr=1)
