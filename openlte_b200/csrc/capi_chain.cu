@@ -36,8 +36,8 @@ extern "C" int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void
     int *d_sn = nullptr;
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_start, start_idx, sizeof(long long) * n_sf, cudaMemcpyHostToDevice, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sn, subfr_num, sizeof(int) * n_sf, cudaMemcpyHostToDevice, stream));
+    if (int rc_ = lteb200_upload_small(ctx, start_idx, sizeof(long long) * n_sf, d_start, stream)) return rc_;
+    if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
     if (rc == LTEB200_OK) rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
     cudaFreeAsync(d_start, stream);
@@ -53,7 +53,7 @@ extern "C" int lteb200_ofdm_demod_batch(lteb200_ctx *ctx, const void *d_iq, int 
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     long long *d_start = nullptr;
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_start, start_idx, sizeof(long long) * n_sf, cudaMemcpyHostToDevice, stream));
+    if (int rc_ = lteb200_upload_small(ctx, start_idx, sizeof(long long) * n_sf, d_start, stream)) return rc_;
     int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
     cudaFreeAsync(d_start, stream);
     return rc;
@@ -68,7 +68,7 @@ extern "C" int lteb200_chan_est_batch(lteb200_ctx *ctx, const float *d_grid, con
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
     int *d_sn = nullptr;
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sn, subfr_num, sizeof(int) * n_sf, cudaMemcpyHostToDevice, stream));
+    if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     int rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
     cudaFreeAsync(d_sn, stream);
     return rc;

@@ -50,6 +50,9 @@ struct lteb200_ctx {
     cudaStream_t s_h2d, s_comp, s_d2h;   // pipeline streams of the host-pointer entry point (lazily created)
     float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)
     long long    cfo_base;
+    // pinned, device-mapped ring for small per-call parameter arrays (see lteb200_upload_small)
+    char        *ring_h, *ring_d;
+    size_t       ring_bytes, ring_off;
     uint32_t    *crc24a_tab;   // x^j mod g(CRC24A) for j < 6168 (lazily built)
     // statistics
     unsigned long long launches;
@@ -73,6 +76,10 @@ struct Bump {
     static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 };
 
+// Small host arrays (per-call subframe numbers, start indices, parameter blocks) -> device memory in stream order WITHOUT using a
+// copy engine: the bytes go into a pinned, device-mapped ring and a one-block kernel copies them.  A cudaMemcpyAsync here would queue
+// behind whatever bulk transfers the caller has in flight on the same DMA engine and stall the compute stream (host pipeline).
+int lteb200_upload_small(lteb200_ctx *ctx, const void *h, size_t bytes, void *d, cudaStream_t stream);
 int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out);
 int lteb200_get_crc24a_tab(lteb200_ctx *ctx, const uint32_t **out);
 

@@ -601,7 +601,7 @@ extern "C" int lteb200_pdcch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
     if (rc) return rc;
     int *d_sn = nullptr;
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sn, subfr_num, sizeof(int) * n_sf, cudaMemcpyHostToDevice, stream));
+    if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     PdcchParams P{12 * N_rb_dl, N_rb_dl};
     const size_t smem = sizeof(int) * (N_HYP * PM_STRIDE + N_HYP * 3 * CC_MAX_N) + sizeof(int16_t) * 6 * 576 + N_HYP * CC_MAX_N;
     static bool attr = false;

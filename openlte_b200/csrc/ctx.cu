@@ -34,6 +34,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->arena_bytes = 0;
     c->launches = 0;
     c->crc24a_tab = nullptr;
+    c->ring_h = c->ring_d = nullptr; c->ring_bytes = c->ring_off = 0;
     c->cfo_hz = 0.f; c->cfo_base = 0;
     c->s_h2d = c->s_comp = c->s_d2h = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
@@ -55,6 +56,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
     if (c->crc24a_tab) cudaFree(c->crc24a_tab);
+    if (c->ring_h) cudaFreeHost(c->ring_h);
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); }
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
@@ -122,5 +124,40 @@ int lteb200_get_crc24a_tab(lteb200_ctx *ctx, const uint32_t **out)
         LTE_CUDA_OK(ctx, cudaMemcpy(ctx->crc24a_tab, t.data(), sizeof(uint32_t) * t.size(), cudaMemcpyHostToDevice));
     }
     *out = ctx->crc24a_tab;
+    return LTEB200_OK;
+}
+
+namespace {
+__global__ void ring_copy_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int n_words)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+int lteb200_upload_small(lteb200_ctx *ctx, const void *h, size_t bytes, void *d, cudaStream_t stream)
+{
+    if (bytes == 0) return LTEB200_OK;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (!ctx->ring_h) {
+        ctx->ring_bytes = 8u << 20;
+        LTE_CUDA_OK(ctx, cudaHostAlloc((void **)&ctx->ring_h, ctx->ring_bytes, cudaHostAllocMapped));
+        LTE_CUDA_OK(ctx, cudaHostGetDevicePointer((void **)&ctx->ring_d, ctx->ring_h, 0));
+        ctx->ring_off = 0;
+    }
+    if (need > ctx->ring_bytes / 4 || ((uintptr_t)d & 3) != 0) {            // large or unaligned: ordinary copy
+        LTE_CUDA_OK(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        return LTEB200_OK;
+    }
+    if (ctx->ring_off + need > ctx->ring_bytes) {
+        // wrap: everything that still reads the old contents was enqueued before this point on streams of this context
+        LTE_CUDA_OK(ctx, cudaDeviceSynchronize());
+        ctx->ring_off = 0;
+    }
+    memcpy(ctx->ring_h + ctx->ring_off, h, bytes);
+    const int n_words = (int)((bytes + 3) / 4);
+    ring_copy_kernel<<<n_words > 4096 ? 8 : 1, 256, 0, stream>>>((const uint32_t *)(ctx->ring_d + ctx->ring_off), (uint32_t *)d, n_words);
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->ring_off += need;
     return LTEB200_OK;
 }

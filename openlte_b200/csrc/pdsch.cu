@@ -221,7 +221,7 @@ static int upload_ints(lteb200_ctx *ctx, const int *h, int n, int **d_out, cudaS
     // small per-call parameter arrays: dedicated allocations cached by size class would be overkill here
     int *d = nullptr;
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d, sizeof(int) * n, stream));
-    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d, h, sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+    if (int rc_ = lteb200_upload_small(ctx, h, sizeof(int) * n, d, stream)) return rc_;
     *d_out = d;
     return LTEB200_OK;
 }

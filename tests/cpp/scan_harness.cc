@@ -33,6 +33,17 @@ int main(int argc, char **argv)
     if (liblte_phy_find_sss(phy, i_buf.data(), q_buf.data(), N_id_2, timing.symb_starts[0], pss_thresh, &N_id_1, &frame_start_idx) != LIBLTE_SUCCESS) { printf("SSS_FAILED\n"); return 1; }
     const uint32 N_id_cell = 3 * N_id_1 + N_id_2;
     printf("sss N_id_1=%u frame_start_idx=%u N_id_cell=%u\n", N_id_1, frame_start_idx, N_id_cell);
+    // MIB: subframe 0 of the detected frame, four-port estimate, bandwidth still unknown (fs.cc:378-386)
+    static LIBLTE_PHY_SUBFRAME_STRUCT sf0;
+    if ((long long)frame_start_idx + phy->N_samps_per_subfr + 2 * phy->N_samps_per_symb + 2 * phy->N_samps_cp_l_0 < (long long)n &&
+        liblte_phy_get_dl_subframe_and_ce(phy, i_buf.data(), q_buf.data(), frame_start_idx, 0, N_id_cell, 4, &sf0) == LIBLTE_SUCCESS) {
+        uint8 mib_ant = 0, mib_off = 0, mib[64];
+        uint32 n_mib = 0;
+        LIBLTE_ERROR_ENUM be = liblte_phy_bch_channel_decode(phy, &sf0, N_id_cell, &mib_ant, mib, &n_mib, &mib_off);
+        printf("bch err=%d N_ant=%u offset=%u bits=", (int)be, mib_ant, mib_off);
+        for (uint32 k = 0; k < n_mib; k++) putchar('0' + mib[k]);
+        putchar('\n');
+    }
     liblte_phy_update_n_rb_dl(phy, LIBLTE_PHY_N_RB_DL_20MHZ);                                   // what the MIB says (fs.cc:417)
     // the frame that starts one frame earlier (uint32 wrap, as the reference computes it) holds an even SFN in this capture
     const uint32 fs0 = frame_start_idx - phy->N_samps_per_frame;

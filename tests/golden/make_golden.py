@@ -114,7 +114,7 @@ def capture_case():
     reference finds in them: coarse timing (20 slots), PSS, SSS, and SIB1 of the frame that starts 15 samples before the
     buffer (sfn even) -- PDCCH decode supplies the allocation, PDSCH decode the 144 transport-block bits."""
     raw = np.fromfile("/root/reference/Test captures/LTE_test_file_int8.bin", dtype=np.int8)
-    N = 340000
+    N = 345000          # through subframe 0 of the frame at 307185 plus the estimator's two look-ahead symbols
     iq = raw[:2 * N].reshape(N, 2).copy()
     i = np.ascontiguousarray(iq[:, 0].astype(np.float32)); q = np.ascontiguousarray(iq[:, 1].astype(np.float32))
     phy = ref.RefPhy(fs=30.72, N_id_cell=0xFFFF, N_ant=4, N_rb_dl=6)
@@ -122,6 +122,11 @@ def capture_case():
     abs_corr = phy.timing_abs_corr(15360)
     err, ss2, nid2, ps, th, f = phy.find_pss(i, q, ss[0])
     err, ss3, nid1, fsi = phy.find_sss(i, q, nid2, ss2, th)
+    # MIB from subframe 0 of the detected frame (LTE_fdd_dl_fs_samp_buf.cc:378-386: four-port estimate, N_rb_dl still 6)
+    sf0 = ref.Subframe()
+    phy.get_dl_subframe_and_ce(i, q, fsi, 0, 3 * nid1 + nid2, 4, sf0)
+    berr, mib_ant, mib_bits, mib_off = phy.bch_decode(sf0, 3 * nid1 + nid2)
+    assert berr == 0
     phy.update_n_rb_dl(100)
     sf = ref.Subframe()
     fs0 = (fsi - 307200) & 0xFFFFFFFF
@@ -134,12 +139,14 @@ def capture_case():
                         pss_thresh=np.float32(th), pss_fo=np.float32(f), sss_ss=ss3, N_id_1=nid1, frame_start_idx=fsi, sib1_frame_start=np.uint32(fs0),
                         cfi=cfi, rnti=a["rnti"], tbs=a["tbs"], mod=a["mod_type"], rv=a["rv_idx"], prb=np.array(a["prb"], np.int32), sib1_bits=bits,
                         sib1_rx_re=sf.rx_symb_re.copy(), sib1_rx_im=sf.rx_symb_im.copy(), sib1_ce_re=sf.rx_ce_re[0, :14].copy(),
-                        sib1_ce_im=sf.rx_ce_im[0, :14].copy())
-    print("capture_cfg1.npz", n, ss[0][0], nid2, ps, th, nid1, fsi, "".join(map(str, bits)))
+                        sib1_ce_im=sf.rx_ce_im[0, :14].copy(), mib_bits=np.asarray(mib_bits[:24], np.uint8), mib_N_ant=mib_ant, mib_offset=mib_off)
+    print("capture_cfg1.npz", n, ss[0][0], nid2, ps, th, nid1, fsi, "".join(map(str, bits)), "MIB", "".join(map(str, mib_bits[:24])), mib_ant, mib_off)
 
 
 if __name__ == "__main__":
     capture_case()
+    if len(sys.argv) > 1 and sys.argv[1] == "capture":
+        sys.exit(0)
     loopback_case("loop_64qam_c0_sf1.npz", 30.72, 100, 0, 1, 3, list(range(12)), 2216, 0x1234)
     loopback_case("loop_qpsk_c77_sf5.npz", 30.72, 100, 77, 5, 1, list(range(40, 76)), 3240, 0x0A0B, N_ant_ce=2, seed=1)
     loopback_case("loop_16qam_c150_sf0.npz", 30.72, 100, 150, 0, 2, list(range(41, 59)), 3112, 0x7FFF, seed=2)

@@ -132,3 +132,21 @@ def test_pdcch_large_batch_is_consistent(ctx):
     base = {s: bytes(raws[i]) for i, s in list(enumerate(sn))[:3]}
     assert all(bytes(raws[b]) == base[sn[b]] for b in range(B))
     assert sum(raws[0].found) >= 3 and raws[0].cfi == cfi
+
+
+def test_mib_of_the_shipped_capture(ctx):
+    """BASELINE config 1: MIB from subframe 0 of the frame the cell search finds in the reference's own capture, through the batched
+    path (int8 I/Q -> OFDM -> four-port estimate at N_rb_dl = 6 -> PBCH): bits 1010100..., one antenna port, SFN mod 4 = 1."""
+    import torch
+    g = gold("capture_cfg1.npz")
+    d_iq = torch.from_numpy(np.ascontiguousarray(g["iq"])).cuda()
+    start = np.array([int(g["frame_start_idx"])], np.int64); sn = np.zeros(1, np.int32)
+    grid = torch.zeros((1, 16, 72, 2), dtype=torch.float32, device="cuda"); ce = torch.zeros((1, 4, 14, 72, 2), dtype=torch.float32, device="cuda")
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ctx.check(ctx.lib.get_dl_subframe_and_ce_batch(ctx.h, dptr(d_iq), 1, g["iq"].shape[0], 4, 6, 0, 4, p(start), p(sn), 1, dptr(grid), dptr(ce), stream_ptr()))
+    out = torch.zeros(C.sizeof(BchResult), dtype=torch.uint8, device="cuda")
+    ctx.check(ctx.lib.bch_decode_batch(ctx.h, dptr(grid), dptr(ce), 6, 0, 1, dptr(out), stream_ptr()))
+    torch.cuda.synchronize()
+    r = BchResult.from_buffer_copy(out.cpu().numpy().tobytes())
+    assert (r.ok, r.N_ant, r.offset) == (1, int(g["mib_N_ant"]), int(g["mib_offset"]))
+    assert np.array_equal(np.frombuffer(bytes(r.bits), np.uint8), g["mib_bits"])

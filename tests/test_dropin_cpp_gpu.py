@@ -35,6 +35,8 @@ def test_scan_on_reference_capture(tmp_path):
     assert "coarse n_corr_peaks=5 symb_start0=2192" in out, out
     assert "pss N_id_2=0 pss_symb=5 freq_offset=0" in out, out
     assert "sss N_id_1=0 frame_start_idx=307185 N_id_cell=0" in out, out
+    mib = "".join(map(str, z["mib_bits"]))
+    assert f"bch err=0 N_ant={int(z['mib_N_ant'])} offset={int(z['mib_offset'])} bits={mib}" in out, out      # MIB 1010100..., BASELINE.md P2
     bits = "".join(map(str, z["sib1_bits"]))
     assert f"pdsch err=0 N_bits=144 bits={bits}" in out, out
     # the allocation found by the PDCCH decode is the one the reference finds, and decoding with it gives the same SIB1
