@@ -227,6 +227,10 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     }
     cudaEvent_t ev_alloc;
     LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    // LTEB200_E2E_TRACE=1: device-side time line of the three streams, printed to stderr (development aid)
+    const bool trace = getenv("LTEB200_E2E_TRACE") != nullptr;
+    cudaEvent_t tr[6] = {};
+    if (trace) for (auto &e : tr) cudaEventCreate(&e);
     void *d_iq = nullptr;
     uint8_t *d_tb = nullptr;
     int32_t *d_ok = nullptr;
@@ -234,6 +238,7 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_iq, samp_bytes * n_samps, ctx->s_comp));
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)n_sf * tb_row, ctx->s_comp));
     LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, ctx->s_comp));
+    if (trace) cudaEventRecord(tr[0], ctx->s_comp);
     LTE_CUDA_OK(ctx, cudaEventRecord(ev_alloc, ctx->s_comp));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_alloc, 0));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_alloc, 0));
@@ -247,7 +252,9 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
             LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * lo, (const char *)h_iq + samp_bytes * lo, samp_bytes * (size_t)(hi - lo),
                                             cudaMemcpyHostToDevice, ctx->s_h2d));
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_h[c], ctx->s_h2d));
+        if (trace && c == 0) cudaEventRecord(tr[1], ctx->s_h2d);
     }
+    if (trace) cudaEventRecord(tr[2], ctx->s_h2d);
     int rc = LTEB200_OK;
     for (int c = 0; c < n_chunks && rc == LTEB200_OK; c++) {
         const int b0 = c * chunk, nb = (n_sf - b0) < chunk ? (n_sf - b0) : chunk;
@@ -256,13 +263,22 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
         rc = lteb200_dl_receive_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx + b0, h_subfr_num + b0, nb, N_pdcch_symbs,
                                       allocs, n_alloc, turbo_mode, n_iter, d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
         if (rc) break;
+        if (trace && c == 0) cudaEventRecord(tr[3], ctx->s_comp);
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_c[c], ctx->s_comp));
         LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_c[c], 0));
         LTE_CUDA_OK(ctx, cudaMemcpyAsync(h_tb_bits + (size_t)b0 * tb_row, d_tb + (size_t)b0 * tb_row, (size_t)nb * tb_row, cudaMemcpyDeviceToHost, ctx->s_d2h));
         LTE_CUDA_OK(ctx, cudaMemcpyAsync(h_crc_ok + (size_t)b0 * n_alloc, d_ok + (size_t)b0 * n_alloc, sizeof(int32_t) * (size_t)nb * n_alloc,
                                         cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
+    if (trace) { cudaEventRecord(tr[4], ctx->s_comp); cudaEventRecord(tr[5], ctx->s_d2h); }
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    if (trace) {
+        float t[6] = {};
+        for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
+        fprintf(stderr, "e2e trace (ms from start): first H2D chunk done %.3f, all H2D done %.3f, first compute chunk done %.3f, all compute done %.3f, all D2H done %.3f (%d chunks of %d)\n",
+                t[1], t[2], t[3], t[4], t[5], n_chunks, chunk);
+        for (auto &e : tr) cudaEventDestroy(e);
+    }
     cudaFreeAsync(d_iq, ctx->s_comp); cudaFreeAsync(d_tb, ctx->s_comp); cudaFreeAsync(d_ok, ctx->s_comp);
     for (int c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_h[c]); cudaEventDestroy(ev_c[c]); }
     cudaEventDestroy(ev_alloc);
