@@ -212,14 +212,41 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     const size_t samp_bytes = iq_fmt == LTEB200_IQ_I8 ? 2 : 8;
     if (!ctx->s_h2d) {
         LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        // the decode kernels (critical path) outrank the front-end kernels of the NEXT chunk, which only fill the gaps they leave
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_comp, cudaStreamNonBlocking, prio_hi));
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo));
         LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
-    int chunk = n_sf / 16;
-    if (const char *e = getenv("LTEB200_E2E_CHUNK")) chunk = atoi(e);
-    if (chunk < 64) chunk = 64;
-    if (chunk > n_sf) chunk = n_sf;
-    const int n_chunks = (n_sf + chunk - 1) / chunk;
+    // Chunk schedule.  Small chunks cost efficiency (partial waves, launch gaps), large ones expose the first copy in and the last
+    // copy out: so the sizes ramp up 128, 256, 512, ... to a plateau and ramp down again at the end.  LTEB200_E2E_CHUNK=n forces
+    // equal chunks of n subframes (development aid).
+    std::vector<int> bounds;                     // chunk c = subframes [bounds[c], bounds[c+1])
+    bounds.push_back(0);
+    if (const char *e = getenv("LTEB200_E2E_CHUNK")) {
+        int chunk = atoi(e);
+        if (chunk < 64) chunk = 64;
+        for (int b = chunk; b < n_sf; b += chunk) bounds.push_back(b);
+    } else if (n_sf >= 1024) {
+        const int plateau = 1024;
+        std::vector<int> head, tail;
+        int used = 0;
+        for (int sz = 128; sz < plateau && used + sz <= n_sf / 2; sz *= 2) { head.push_back(sz); used += sz; }
+        for (int sz = 128; sz < plateau && used + sz <= (n_sf * 3) / 4; sz *= 2) { tail.push_back(sz); used += sz; }
+        int mid = n_sf - used, pos = 0;
+        for (int sz : head) { pos += sz; bounds.push_back(pos); }
+        const int n_mid = (mid + plateau - 1) / plateau;
+        for (int i = 1; i <= n_mid; i++) bounds.push_back(pos + (int)((long long)mid * i / n_mid));
+        pos += mid;
+        for (int i = (int)tail.size() - 1; i > 0; i--) { pos += tail[i]; bounds.push_back(pos); }
+    } else if (n_sf >= 256) {
+        for (int i = 1; i < 4; i++) bounds.push_back(n_sf * i / 4);
+    }
+    if (bounds.back() != n_sf) bounds.push_back(n_sf);
+    const int n_chunks = (int)bounds.size() - 1;
+    // a subframe's 16 symbols end two symbols into the next subframe (the estimator's look-ahead): that halo travels with the chunk
+    const long long halo = 2LL * ((128LL << fs_idx) + (10LL << fs_idx)) + 16;
     std::vector<cudaEvent_t> ev_h(n_chunks), ev_c(n_chunks);
     for (int c = 0; c < n_chunks; c++) {
         LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_h[c], cudaEventDisableTiming));
@@ -231,6 +258,7 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     const bool trace = getenv("LTEB200_E2E_TRACE") != nullptr;
     cudaEvent_t tr[6] = {};
     if (trace) for (auto &e : tr) cudaEventCreate(&e);
+    std::vector<cudaEvent_t> tr_c0, tr_c1;
     void *d_iq = nullptr;
     uint8_t *d_tb = nullptr;
     int32_t *d_ok = nullptr;
@@ -242,28 +270,46 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     LTE_CUDA_OK(ctx, cudaEventRecord(ev_alloc, ctx->s_comp));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_alloc, 0));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_alloc, 0));
-    // stage 1: sample slices, back to back.  Chunk c owns [start(c), start(c+1)); the last one runs to the end of the buffer.
+    // stage 1: sample slices, back to back.  Chunk c's copy ends `halo` samples into chunk c+1; the next copy continues from there.
+    long long copied = 0;
     for (int c = 0; c < n_chunks; c++) {
-        long long lo = c == 0 ? 0 : h_start_idx[(size_t)c * chunk];
-        long long hi = c + 1 < n_chunks ? h_start_idx[(size_t)(c + 1) * chunk] : n_samps;
-        if (lo < 0) lo = 0;
+        long long hi = c + 1 < n_chunks ? h_start_idx[bounds[c + 1]] + halo : n_samps;
         if (hi > n_samps) hi = n_samps;
-        if (hi > lo)
-            LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * lo, (const char *)h_iq + samp_bytes * lo, samp_bytes * (size_t)(hi - lo),
+        if (hi > copied) {
+            LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * copied, (const char *)h_iq + samp_bytes * copied, samp_bytes * (size_t)(hi - copied),
                                             cudaMemcpyHostToDevice, ctx->s_h2d));
+            copied = hi;
+        }
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_h[c], ctx->s_h2d));
         if (trace && c == 0) cudaEventRecord(tr[1], ctx->s_h2d);
     }
     if (trace) cudaEventRecord(tr[2], ctx->s_h2d);
+    // stage 2 is split over two streams: OFDM + channel estimate of chunk c+1 (s_front) may run while the decode kernel of chunk c
+    // (s_comp) drains its last wave, so the tail of one chunk is filled with the head of the next.
     int rc = LTEB200_OK;
+    const int nsc = 12 * N_rb_dl;
+    std::vector<cudaEvent_t> ev_f(n_chunks);
+    for (int c = 0; c < n_chunks; c++) LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_f[c], cudaEventDisableTiming));
+    LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_front, ev_alloc, 0));
     for (int c = 0; c < n_chunks && rc == LTEB200_OK; c++) {
-        const int b0 = c * chunk, nb = (n_sf - b0) < chunk ? (n_sf - b0) : chunk;
-        // a chunk's last subframe looks two symbols into the next chunk's samples: wait for that copy too
-        LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_comp, ev_h[c + 1 < n_chunks ? c + 1 : c], 0));
-        rc = lteb200_dl_receive_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx + b0, h_subfr_num + b0, nb, N_pdcch_symbs,
-                                      allocs, n_alloc, turbo_mode, n_iter, d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
+        const int b0 = bounds[c], nb = bounds[c + 1] - b0;
+        float *d_grid = nullptr, *d_ce = nullptr;
+        LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_front, ev_h[c], 0));
+        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)nb, ctx->s_front));
+        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)nb * N_ant, ctx->s_front));
+        rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx + b0, h_subfr_num + b0, nb, d_grid, d_ce,
+                                                  ctx->s_front);
         if (rc) break;
+        LTE_CUDA_OK(ctx, cudaEventRecord(ev_f[c], ctx->s_front));
+        LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_comp, ev_f[c], 0));
+        if (trace) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tr_c0.push_back(a); tr_c1.push_back(b); cudaEventRecord(a, ctx->s_comp); }
+        rc = lteb200_pdsch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, h_subfr_num + b0, nb, N_pdcch_symbs, allocs, n_alloc, turbo_mode, n_iter,
+                                        d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
+        if (rc) break;
+        cudaFreeAsync(d_grid, ctx->s_comp);
+        cudaFreeAsync(d_ce, ctx->s_comp);
         if (trace && c == 0) cudaEventRecord(tr[3], ctx->s_comp);
+        if (trace) cudaEventRecord(tr_c1[c], ctx->s_comp);
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_c[c], ctx->s_comp));
         LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_c[c], 0));
         LTE_CUDA_OK(ctx, cudaMemcpyAsync(h_tb_bits + (size_t)b0 * tb_row, d_tb + (size_t)b0 * tb_row, (size_t)nb * tb_row, cudaMemcpyDeviceToHost, ctx->s_d2h));
@@ -272,15 +318,23 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     }
     if (trace) { cudaEventRecord(tr[4], ctx->s_comp); cudaEventRecord(tr[5], ctx->s_d2h); }
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(ctx->s_comp), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    { const cudaError_t e4 = cudaStreamSynchronize(ctx->s_front); if (e2 == cudaSuccess) e2 = e4; }
     if (trace) {
         float t[6] = {};
         for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
-        fprintf(stderr, "e2e trace (ms from start): first H2D chunk done %.3f, all H2D done %.3f, first compute chunk done %.3f, all compute done %.3f, all D2H done %.3f (%d chunks of %d)\n",
-                t[1], t[2], t[3], t[4], t[5], n_chunks, chunk);
+        fprintf(stderr, "e2e trace (ms from start): first H2D chunk done %.3f, all H2D done %.3f, first compute chunk done %.3f, all compute done %.3f, all D2H done %.3f (%d chunks, first %d subframes)\n",
+                t[1], t[2], t[3], t[4], t[5], n_chunks, bounds[1]);
+        for (size_t c = 0; c < tr_c0.size(); c++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tr[0], tr_c0[c]); cudaEventElapsedTime(&b, tr[0], tr_c1[c]);
+            fprintf(stderr, "  chunk %zu: %d subframes, compute %.3f -> %.3f ms (%.3f ms, %.2f us/subframe)\n", c, bounds[c + 1] - bounds[c], a, b, b - a,
+                    1e3 * (b - a) / (bounds[c + 1] - bounds[c]));
+            cudaEventDestroy(tr_c0[c]); cudaEventDestroy(tr_c1[c]);
+        }
         for (auto &e : tr) cudaEventDestroy(e);
     }
     cudaFreeAsync(d_iq, ctx->s_comp); cudaFreeAsync(d_tb, ctx->s_comp); cudaFreeAsync(d_ok, ctx->s_comp);
-    for (int c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_h[c]); cudaEventDestroy(ev_c[c]); }
+    for (int c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_h[c]); cudaEventDestroy(ev_c[c]); cudaEventDestroy(ev_f[c]); }
     cudaEventDestroy(ev_alloc);
     if (rc == LTEB200_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
         lteb200_set_error(ctx, "dl_receive_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));

@@ -47,7 +47,7 @@ struct lteb200_ctx {
     std::map<int, QppTables> qpp;
     std::map<int, MlmTables> mlm;
     std::map<std::vector<int>, RateUnmatchMap> rum;
-    cudaStream_t s_h2d, s_comp, s_d2h;   // pipeline streams of the host-pointer entry point (lazily created)
+    cudaStream_t s_h2d, s_comp, s_d2h, s_front;   // pipeline streams of the host-pointer entry point (lazily created)
     float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)
     long long    cfo_base;
     // pinned, device-mapped ring for small per-call parameter arrays (see lteb200_upload_small)

@@ -36,7 +36,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->crc24a_tab = nullptr;
     c->ring_h = c->ring_d = nullptr; c->ring_bytes = c->ring_off = 0;
     c->cfo_hz = 0.f; c->cfo_base = 0;
-    c->s_h2d = c->s_comp = c->s_d2h = nullptr;
+    c->s_h2d = c->s_comp = c->s_d2h = c->s_front = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
     // otherwise every host-pointer call would re-acquire gigabytes from the driver.
@@ -57,7 +57,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     if (c->arena) cudaFree(c->arena);
     if (c->crc24a_tab) cudaFree(c->crc24a_tab);
     if (c->ring_h) cudaFreeHost(c->ring_h);
-    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); }
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_front); }
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
     for (auto &kv : c->rum) cudaFree(kv.second.first_k);
