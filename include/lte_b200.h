@@ -215,6 +215,21 @@ int lteb200_pdcch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, cons
                                  float phich_res, int phich_dur, uint32_t *cfi, uint32_t *N_symbs, lteb200_dci *allocs,
                                  uint32_t *N_alloc);
 
+/* The scan loop (LTE_fdd_dl_fs_samp_buf.cc:491-515) for n_sf subframes in one call: front end, PDCCH decode, and PDSCH decode of
+ * every allocation a subframe's PDCCH announced (N_ant == 1).  d_iq: DEVICE samples; start_idx, subfr_num, results, tb_bits: HOST.
+ * Transport-block bits (one per byte) are appended to tb_bits; results[b].tb_offset[a] is where allocation a of subframe b starts
+ * (-1: CRC failed or nothing decodable).  Synchronises `stream` (the DCI contents decide what is launched next). */
+typedef struct {
+    int32_t     cfi, N_symbs, N_alloc;
+    int32_t     pdcch_err;       /* return value of lteb200_pdcch_unpack for this subframe */
+    lteb200_dci dci[6];
+    int32_t     crc_ok[6];
+    long long   tb_offset[6];
+} lteb200_scan_result;
+int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl, int N_id_cell, int N_ant,
+                          float phich_res, const long long *start_idx, const int *subfr_num, int n_sf, int turbo_mode, int n_iter,
+                          lteb200_scan_result *results, uint8_t *tb_bits, long long tb_capacity, long long *tb_used, void *stream);
+
 /* -------------------------------------------------------------------------------------------- front end */
 /* LTE_fdd_dl_fs_samp_buf::freq_shift (LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713) and the int8 -> float
  * conversion of copy_input_to_samp_buf (:657-694).  d_iq_in: DEVICE samples in iq_fmt; d_iq_out: DEVICE float2 [n_samps].

@@ -54,6 +54,12 @@ class Dci(C.Structure):
                     tx_mode=int(a.tx_mode), chan_type=0, prb=[int(a.prb[0][j]) for j in range(n)], prb1=[int(a.prb[1][j]) for j in range(n)])
 
 
+class ScanResult(C.Structure):
+    """lteb200_scan_result"""
+    _fields_ = [("cfi", C.c_int32), ("N_symbs", C.c_int32), ("N_alloc", C.c_int32), ("pdcch_err", C.c_int32), ("dci", Dci * 6), ("crc_ok", C.c_int32 * 6),
+                ("tb_offset", C.c_longlong * 6)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/lte_b200.h
 _vp, _i, _ll, _u32, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_uint32, C.c_float
 SYMBOLS = {
@@ -83,6 +89,7 @@ SYMBOLS = {
     "lteb200_pdcch_decode_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp, _vp]),
     "lteb200_pdcch_unpack": (_i, [_vp, _i, _i, _vp, _vp]),
     "lteb200_pdcch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _u32, C.c_uint8, _f, _i, _vp, _vp, _vp, _vp]),
+    "lteb200_dl_scan_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
     "lteb200_freq_shift_batch": (_i, [_vp, _vp, _i, _ll, _ll, _f, _i, _vp, _vp]),
     "lteb200_freq_shift": (_i, [_vp, _vp, _vp, _u32, _u32, _f, _i]),
     "lteb200_set_freq_offset": (_i, [_vp, _f, _ll]),

@@ -106,7 +106,7 @@ def pieces():
     np.savez_compressed(os.path.join(HERE, "control_pieces_ref.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "scan"):
     # the reference prints a line for every DCI 1A whose first bit says "format 0": keep the terminal readable
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
@@ -117,3 +117,94 @@ if __name__ == "__main__":
         os.dup2(saved, 1)
     bch_cases()
     pdcch_cases()
+
+
+# ------------------------------------------------------------------------------------------------------------ scan loop
+def scan_subframe(phy, i, q, frame_start, sn, cell):
+    """One iteration of the reference's scan loop (LTE_fdd_dl_fs_samp_buf.cc:491-515): front end, PDCCH decode, PDSCH decode of
+    every allocation found.  Returns the row the fixtures store."""
+    sf = ref.Subframe(); sf.clear()
+    phy.get_dl_subframe_and_ce(i, q, frame_start & 0xFFFFFFFF, sn, cell, 1, sf)
+    err, cfi, nsym, allocs = phy.pdcch_decode2(sf, cell, 1)
+    tbs_bits = []
+    oks = []
+    if err == 0:
+        for a in allocs:
+            if a["N_prb"] < 1 or a["tbs"] < 1 or a["prb"] != a["prb1"]:
+                oks.append(0); tbs_bits.append(np.zeros(0, np.uint8)); continue
+            e2, bits = phy.pdsch_decode(sf, nsym, cell, 1, a["mod_type"], a["prb"], a["tbs"], a["rnti"], rv=a["rv_idx"], tx_mode=a["tx_mode"])
+            oks.append(1 if e2 == 0 else 0); tbs_bits.append(bits if e2 == 0 else np.zeros(0, np.uint8))
+    return err, cfi, nsym, allocs, oks, tbs_bits
+
+
+def store_scan(out, tag, rows):
+    out[f"{tag}_n"] = np.int32(len(rows))
+    for k, (err, cfi, nsym, allocs, oks, bits) in enumerate(rows):
+        out[f"{tag}_hdr_{k}"] = np.array([err, cfi, nsym, len(allocs)], np.int32)
+        out[f"{tag}_allocs_{k}"] = alloc_rows(allocs)
+        out[f"{tag}_ok_{k}"] = np.array(oks, np.int32)
+        for a, b in enumerate(bits):
+            out[f"{tag}_bits_{k}_{a}"] = np.asarray(b, np.uint8)
+
+
+def scan_cases():
+    out = {}
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1)
+    # A: the shipped capture, subframes 1..9 of the frame that starts 15 samples before the buffer
+    z = np.load(os.path.join(HERE, "capture_cfg1.npz"))
+    iq = z["iq"]; i = np.ascontiguousarray(iq[:, 0].astype(np.float32)); q = np.ascontiguousarray(iq[:, 1].astype(np.float32))
+    fs0 = int(z["frame_start_idx"]) - 307200
+    phy = ref.RefPhy(fs=30.72, N_id_cell=0, N_ant=1, N_rb_dl=100)
+    os.dup2(devnull, 1)
+    try:
+        rows = [scan_subframe(phy, i, q, fs0, sn, 0) for sn in range(1, 10)]
+    finally:
+        os.dup2(saved, 1)
+    store_scan(out, "cap", rows)
+    out["cap_frame_start"] = np.int64(fs0)
+    print("capture scan:", [(r[0], r[1], len(r[3]), r[4]) for r in rows])
+    # B: synthetic 10 MHz stream from the reference's transmitter: DCI 1A + the PDSCH it announces, four subframes + CRS-only tail
+    rng = np.random.default_rng(21)
+    nrb, cell, fs, n_s = 50, 23, 15.36, 15360
+    phy = ref.RefPhy(fs=fs, N_id_cell=cell, N_ant=1, N_rb_dl=nrb)
+    plan = {1: (2, [dict(rnti=0xFFFF, mcs=5, N_prb=6, prb0=3)]),
+            2: (3, [dict(rnti=0xFFFE, mcs=9, N_prb=8, prb0=10), dict(rnti=7, mcs=1, N_prb=2, prb0=30)]),
+            3: (1, []),
+            4: (2, [dict(rnti=0xFFFF, mcs=2, N_prb=3, prb0=40)])}
+    total = 6 * n_s + 4096
+    si = np.zeros(total, np.float32); sq = np.zeros(total, np.float32)
+    tx_bits = {}
+    for sn in range(1, 6):
+        sf = ref.Subframe(); sf.clear(); sf.set_num(sn)
+        phy.map_crs(sf, cell, 1)
+        if sn in plan:
+            cfi, allocs = plan[sn]
+            for a in allocs:
+                tbs = ref.tbs_71721(a["mcs"], 3)
+                tb = rng.integers(0, 2, tbs).astype(np.uint8); tx_bits[(sn, a["rnti"])] = tb
+                nsym = cfi
+                assert phy.pdsch_encode(sf, nsym, cell, 1, 1, list(range(a["prb0"], a["prb0"] + a["N_prb"])), tbs, a["rnti"], tb) == 0
+            assert phy.pdcch_encode(sf, cell, 1, cfi, allocs) == 0
+        a_i, a_q = phy.create_dl_subframe(sf, 0, n_s)
+        si[sn * n_s:(sn + 1) * n_s] = a_i; sq[sn * n_s:(sn + 1) * n_s] = a_q
+    z_ = (si + 1j * sq) * (0.8 * np.exp(0.4j)) + 0.01 * (rng.standard_normal(total) + 1j * rng.standard_normal(total))
+    sc = 100.0 / max(np.abs(z_.real).max(), np.abs(z_.imag).max())
+    i8 = np.stack([np.rint(z_.real * sc), np.rint(z_.imag * sc)], -1).astype(np.int8)
+    i = np.ascontiguousarray(i8[:, 0].astype(np.float32)); q = np.ascontiguousarray(i8[:, 1].astype(np.float32))
+    os.dup2(devnull, 1)
+    try:
+        rows = [scan_subframe(phy, i, q, 0, sn, cell) for sn in range(1, 5)]
+    finally:
+        os.dup2(saved, 1)
+    store_scan(out, "syn", rows)
+    out["syn_iq"] = i8; out["syn_cfg"] = np.array([nrb, cell, 3], np.int32)      # N_rb_dl, cell, fs_idx
+    print("synthetic scan:", [(r[0], r[1], len(r[3]), r[4]) for r in rows])
+    for k, sn in enumerate(range(1, 5)):
+        for a, al in enumerate(rows[k][3]):
+            if rows[k][4][a] and (sn, al["rnti"]) in tx_bits:
+                assert np.array_equal(rows[k][5][a], tx_bits[(sn, al["rnti"])]), (sn, al["rnti"])
+    np.savez_compressed(os.path.join(HERE, "control_scan_ref.npz"), **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "scan":
+    scan_cases()
