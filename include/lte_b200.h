@@ -230,6 +230,17 @@ int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_fmt, long l
                           float phich_res, const long long *start_idx, const int *subfr_num, int n_sf, int turbo_mode, int n_iter,
                           lteb200_scan_result *results, uint8_t *tb_bits, long long tb_capacity, long long *tb_used, void *stream);
 
+/* ------------------------------------------------------------------------------------------ transmit side */
+/* Batched downlink transmitter for test-signal generation: liblte_phy_map_crs (liblte_phy.h:1031) +
+ * liblte_phy_pdsch_channel_encode (liblte_phy.h:716-724, liblte_phy.cc:3489-3680) for every allocation + liblte_phy_create_dl_subframe
+ * (liblte_phy.h:1109, liblte_phy.cc:5862) for n_sf subframes.  d_tb_bits: DEVICE [n_sf][n_alloc][tb_stride], one bit per byte.
+ * d_grid (optional, DEVICE [n_sf][14][12*N_rb_dl] float2) receives the resource grids, d_iq (optional, DEVICE
+ * [n_sf][1920 << fs_idx] float2) the time-domain subframes back to back.  One antenna port; transport blocks with TBS + 24 in the
+ * turbo interleaver table (the reference's encoder produces no filler bits); the reference's wrapped interleaver. */
+int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_bits, int tb_stride, const lteb200_alloc *allocs, int n_alloc, int fs_idx,
+                              int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
+                              float *d_iq, void *stream);
+
 /* -------------------------------------------------------------------------------------------- front end */
 /* LTE_fdd_dl_fs_samp_buf::freq_shift (LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713) and the int8 -> float
  * conversion of copy_input_to_samp_buf (:657-694).  d_iq_in: DEVICE samples in iq_fmt; d_iq_out: DEVICE float2 [n_samps].

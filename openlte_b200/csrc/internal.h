@@ -4,3 +4,17 @@
 
 int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream);
 int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, cudaStream_t stream);
+
+// Per-(cell, allocation, CFI) tables of the PDSCH symbol level, shared by the receive and the transmit side (pdsch.cu)
+struct AllocTables {
+    int *re_idx;      // [3][idx_stride]
+    int idx_stride;
+    int M[3];
+    uint8_t *cseq;    // [10][c_stride]
+    int c_stride;
+    int Qm, K, F;
+};
+int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc &al, AllocTables *out);
+int get_twiddles(lteb200_ctx *ctx, int N, float2 **out);                 // e^{-2 pi i k/N}, k < N (ofdm.cu)
+int get_crs_table(lteb200_ctx *ctx, int N_id_cell, float2 **out);        // [20][3][220] (chanest.cu)
+int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv, RateUnmatchMap *out);

@@ -8,6 +8,7 @@
 // coalesced to the resource grid.  Twiddles come from a table computed in double precision on the host.
 // HBM-bound by design: per symbol it reads N*8 B (2 B/sample for int8 input) and writes 12*N_rb*8 B.
 #include "common.cuh"
+#include "fft_dev.cuh"
 #include <math.h>
 
 namespace {
@@ -40,10 +41,6 @@ template <> __device__ __forceinline__ float2 load_iq<char2>(const char2 *p, lon
     return make_float2((float)v.x, (float)v.y);
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
-{
-    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
-}
 
 // grid: [n_sf][16][nsc] float2.  blockIdx.x = subframe * 16 + symbol.
 // WINDOWS == false: blockIdx.x = subframe*16 + symbol, start_idx[subframe] is the subframe start.
@@ -68,38 +65,7 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
         bufA[i] = v;
     }
     __syncthreads();
-    // Stockham autosort, decimation in frequency.  n = remaining transform length, s = stride.
-    float2 *src = bufA, *dst = bufB;
-    int n = P.N, s = 1;
-    while (n > 1) {
-        if ((n & 3) == 0) {
-            const int n1 = n >> 2;
-            for (int t = threadIdx.x; t < (P.N >> 2); t += blockDim.x) {
-                const int p = t / s, q = t - p * s;   // p in [0,n1), q in [0,s)
-                const float2 a = src[q + s * p], b = src[q + s * (p + n1)], c = src[q + s * (p + 2 * n1)], d = src[q + s * (p + 3 * n1)];
-                const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
-                const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
-                const float2 jbmd = make_float2(bmd.y, -bmd.x);  // -j*(b-d) for the forward transform
-                const float2 w1 = tw[p * s], w2 = tw[2 * p * s], w3 = tw[3 * p * s];
-                dst[q + s * (4 * p + 0)] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-                dst[q + s * (4 * p + 1)] = cmul(make_float2(amc.x + jbmd.x, amc.y + jbmd.y), w1);
-                dst[q + s * (4 * p + 2)] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), w2);
-                dst[q + s * (4 * p + 3)] = cmul(make_float2(amc.x - jbmd.x, amc.y - jbmd.y), w3);
-            }
-            n >>= 2; s <<= 2;
-        } else {
-            const int n1 = n >> 1;
-            for (int t = threadIdx.x; t < (P.N >> 1); t += blockDim.x) {
-                const int p = t / s, q = t - p * s;
-                const float2 a = src[q + s * p], b = src[q + s * (p + n1)];
-                dst[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
-                dst[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[p * s]);
-            }
-            n >>= 1; s <<= 1;
-        }
-        __syncthreads();
-        float2 *t_ = src; src = dst; dst = t_;
-    }
+    float2 *src = stockham_forward(bufA, bufB, P.N, tw);
     // bins -> subcarriers (:8625-8634): symb[h+i] = X[i+1], symb[h-1-i] = X[N-1-i]
     float2 *out = grid + (WINDOWS ? (size_t)blockIdx.x : ((size_t)sf * 16 + sym)) * P.nsc;
     for (int k = threadIdx.x; k < 2 * P.h; k += blockDim.x) {
@@ -268,7 +234,7 @@ struct FftTwiddles { float2 *tw; };
 static std::map<std::pair<int, int>, float2 *> g_tw;  // (device, N) -> table
 static std::mutex g_tw_mu;
 
-static int get_twiddles(lteb200_ctx *ctx, int N, float2 **out)
+int get_twiddles(lteb200_ctx *ctx, int N, float2 **out)
 {
     std::lock_guard<std::mutex> lk(g_tw_mu);
     auto key = std::make_pair(ctx->device, N);

@@ -172,18 +172,10 @@ int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, co
                             float *d_out, cudaStream_t stream);
 
 // Per-allocation device tables, cached in the context by content.
-struct AllocTables {
-    int *re_idx;      // [3][idx_stride]
-    int idx_stride;
-    int M[3];
-    uint8_t *cseq;    // [10][c_stride]
-    int c_stride;
-    int Qm, K, F;
-};
 static std::map<std::vector<int>, AllocTables> g_alloc_tabs;
 static std::mutex g_alloc_mu;
 
-static int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc &al, AllocTables *out)
+int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc &al, AllocTables *out)
 {
     if (al.N_prb < 1 || al.N_prb > N_rb_dl || al.mod_type < 0 || al.mod_type > 3) { lteb200_set_error(ctx, "bad allocation"); return LTEB200_ERR_ARGS; }
     for (int s = 0; s < 2; s++)
