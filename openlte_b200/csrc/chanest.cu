@@ -20,9 +20,12 @@ constexpr double PI_D = 3.14159265358979323846;
 
 __device__ __forceinline__ float wrap_phase(float p1, float p2)
 {
-    // liblte_phy.cc:14105-14116: float difference, compared and corrected in double
-    while ((double)__fsub_rn(p1, p2) >= PI_D) p1 = (float)((double)p1 - 2 * PI_D);
-    while ((double)__fsub_rn(p1, p2) <= -PI_D) p1 = (float)((double)p1 + 2 * PI_D);
+    // liblte_phy.cc:14105-14116: float difference, compared and corrected in double.  A float f satisfies (double)f >= pi exactly
+    // when f >= 0x40490FDB (the float just above pi; the one below, 0x40490FDA, is smaller than pi), so the comparison is done in
+    // float; the rarely taken correction stays in double.
+    const float PI_UP = __uint_as_float(0x40490FDBu);
+    while (__fsub_rn(p1, p2) >= PI_UP) p1 = (float)((double)p1 - 2 * PI_D);
+    while (__fsub_rn(p1, p2) <= -PI_UP) p1 = (float)((double)p1 + 2 * PI_D);
     return p1;
 }
 
@@ -79,10 +82,15 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
         float *A = Ag + i * 1200;
         const int of = crs_off(p, i, vsh);
         float prev = A[of];
-        for (int j = 1; j < n_crs; j++) {
-            const int k = 6 * j + of;
-            prev = wrap_phase(A[k], prev);
-            A[k] = prev;
+        // eight tones per round: loads first, then the dependent chain on registers, then the stores (no shared-memory latency on the chain)
+        for (int j0 = 1; j0 < n_crs; j0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (j0 + u < n_crs) ? A[6 * (j0 + u) + of] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (j0 + u < n_crs) { prev = wrap_phase(v[u], prev); v[u] = prev; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (j0 + u < n_crs) A[6 * (j0 + u) + of] = v[u];
         }
     }
     __syncthreads();

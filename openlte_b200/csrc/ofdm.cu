@@ -132,7 +132,10 @@ template <> struct Dft<16> {
 // One Stockham pass of radix R over a transform of current length n and stride s (n * s == N); thread `tid` handles
 // butterflies tid, tid + NTHR, ...  SRC_GLOBAL: inputs come from the sample stream (first pass); DST_GRID: outputs go
 // to the resource grid through the bin -> subcarrier map (last pass, where p == 0 and no twiddle applies).
-template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID, bool CFO = false>
+// PAD_SRC / PAD_DST: the shared buffer is indexed through pad16() (one spare element per 16): the first pass writes 16 consecutive
+// elements per thread, which without the padding puts every lane of a warp on the same banks.
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID, bool CFO = false, bool PAD_SRC = false, bool PAD_DST = false>
 __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long long w0, long long n_samps, const float2 *__restrict__ src,
                                               float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid,
                                               float cfo_hz = 0.f, double cfo_fs = 1.0, long long cfo_base = 0)
@@ -150,7 +153,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
                 const long long sidx = w0 + i;
                 x[k] = (sidx >= 0 && sidx < n_samps) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
                 if (CFO) x[k] = cfo_rotate(x[k], cfo_base + sidx, cfo_hz, cfo_fs);
-            } else x[k] = src[i];
+            } else x[k] = src[PAD_SRC ? pad16(i) : i];
         }
         Dft<R>::run(x);
 #pragma unroll
@@ -161,7 +164,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
                 else if (bin >= N - h) out[bin - (N - h)] = x[k];
             } else {
                 const float2 v = (k == 0 || p == 0) ? x[k] : cmul(x[k], __ldg(&tw[p * k * s]));
-                dst[q + s * (R * p + k)] = v;
+                dst[PAD_DST ? pad16(q + s * (R * p + k)) : q + s * (R * p + k)] = v;
             }
         }
     }
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(N / 16 < 32 ? 32 : N / 16)
 ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
                       const float2 *__restrict__ tw, float2 *__restrict__ grid)
 {
-    __shared__ float2 bufA[N], bufB[N];
+    __shared__ float2 bufA[N + N / 16], bufB[N];
     const int tid = threadIdx.x;
     const int sf = blockIdx.x >> 4, sym = blockIdx.x & 15;
     const int slot = sym / 7, l = sym % 7;
@@ -181,31 +184,31 @@ ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long lo
     float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
     const bool act = tid < N / 16;
     if constexpr (N == 2048) {          // 16 x 16 x 8
-        if (act) stockham_pass<N, 16, 2048, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 2048, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
-        if (act) stockham_pass<N, 16, 128, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 128, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 1024) {   // 16 x 16 x 4
-        if (act) stockham_pass<N, 16, 1024, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 1024, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
-        if (act) stockham_pass<N, 16, 64, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 64, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 512) {    // 16 x 8 x 4
-        if (act) stockham_pass<N, 16, 512, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 512, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
-        if (act) stockham_pass<N, 8, 32, T, false, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 8, 32, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 256) {    // 16 x 16
-        if (act) stockham_pass<N, 16, 256, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 256, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
-        if (act) stockham_pass<N, 16, 16, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 16, 16, T, false, true, false, true, false>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     } else {                  // 128 = 16 x 8
-        if (act) stockham_pass<N, 16, 128, T, true, false, CFO>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) stockham_pass<N, 16, 128, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
         __syncthreads();
-        if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
+        if (act) stockham_pass<N, 8, 8, T, false, true, false, true, false>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     }
 }
 
