@@ -142,3 +142,30 @@ def test_empty_and_degenerate_batches(ctx):
     ctx.check(ctx.lib.turbo_decode_batch(ctx.h, dptr(s), 40, 2, 0, 0, dptr(o[:2]), None))
     torch.cuda.synchronize()
     assert bool((o[:2] == 0).all())
+
+
+def test_utilities_gold_sequence_and_crc_check(ctx, port):
+    """lteb200_prs_c_batch (generate_prs_c) and lteb200_crc24a_check_batch (calc_crc) against the oracle."""
+    import torch
+    import ctypes as C
+    from util import dptr, stream_ptr
+    for c_init, n in ((0, 100), ((0x1234 << 14) | (7 << 9) | 301, 20000), (0x7FFFFFFF, 31)):
+        d = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ctx.check(ctx.lib.prs_c_batch(ctx.h, C.c_uint32(c_init), n, dptr(d), stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), port.prs_c(c_init, n))
+    rng = np.random.default_rng(2)
+    for tbs in (16, 144, 1000, 6120):
+        n, stride = 37, tbs + 24 + 5
+        blocks = np.zeros((n, stride), np.uint8)
+        blocks[:, :tbs] = rng.integers(0, 2, (n, tbs))
+        want = np.ones(n, np.int32)
+        for b in range(n):
+            crc = port.crc(blocks[b, :tbs])
+            blocks[b, tbs:tbs + 24] = [(crc >> (23 - i)) & 1 for i in range(24)]
+            if b % 3 == 1:
+                blocks[b, rng.integers(0, tbs + 24)] ^= 1; want[b] = 0
+        d = torch.from_numpy(blocks).cuda(); ok = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        ctx.check(ctx.lib.crc24a_check_batch(ctx.h, dptr(d), stride, tbs, n, dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(ok.cpu().numpy(), want), tbs
