@@ -328,9 +328,12 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = ctx.launches - l0
     # ---- timed: end to end through the host-pointer C-ABI call
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    # the host-pointer leg shares the host (memory bandwidth, PCIe root ports, CPU time) with whatever else runs on the box: the K-step
+    # measurement is repeated three times and the median is reported, all three are listed
+    e2e_runs = [timed(step_e2e, args.steps) for _ in range(3)]
+    ms_e2e = sorted(e2e_runs)[1]
     clocks = sampler.stop()
     e2e_ok = bool((h_ok.numpy() == 1).all()) and bool(np.array_equal(h_tb.numpy(), want))
 
@@ -426,7 +429,8 @@ def main():
                           "input_bytes_per_step_per_gpu": int(iq.nbytes), "l2_policy": "inputs larger than L2 (%.0f MB > 126 MB)" % (iq.nbytes / 1e6),
                           "parallelism": f"{world} independent replicas, no data-path collective"},
                "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "subframes/s", "h2d_bytes_per_step": int(iq.nbytes), "d2h_bytes_per_step": int(h_tb.numel() + h_ok.numel() * 4),
-                       "ms_per_step": round(ms_e2e / args.steps, 4), "api": "lteb200_dl_receive_host (host pointers)", "host_placement": numa_note, "results_ok": e2e_ok},
+                       "ms_per_step": round(ms_e2e / args.steps, 4), "api": "lteb200_dl_receive_host (host pointers)", "host_placement": numa_note,
+                       "timing": "median of 3 repeats of %d steps" % args.steps, "ms_per_step_all_repeats": [round(x / args.steps, 4) for x in e2e_runs], "results_ok": e2e_ok},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
                "validity": {"crc_pass_frac": crc_frac, "bits_equal_transmitted": bits_equal}}
         print(json.dumps(out))
