@@ -59,7 +59,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     if (c->ring_h) cudaFreeHost(c->ring_h);
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_front); }
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
-    for (auto &kv : c->mlm) { cudaFree(kv.second.piT); cudaFree(kv.second.csr_start); cudaFree(kv.second.csr_pos); }
+    for (auto &kv : c->mlm) cudaFree(kv.second.piT);   // one blob: piT | csr_start | csr_pos
     for (auto &kv : c->rum) cudaFree(kv.second.first_k);
     delete c;
 }

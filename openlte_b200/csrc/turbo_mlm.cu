@@ -23,6 +23,39 @@
 
 namespace {
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the per-block-size tables into shared memory, completion on an mbarrier: the copy
+// engine stages the 37 KB of interleaver tables while the CTA's threads are busy with the input phase.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// the mbarrier exists only in the kernels that use the bulk copy
+template <bool FUSED> __device__ __forceinline__ uint64_t *table_barrier() { __shared__ __align__(8) uint64_t bar; return &bar; }
+template <> __device__ __forceinline__ uint64_t *table_barrier<true>() { return nullptr; }
+
 constexpr int NEG = -8000;
 constexpr int LE_LIM = 1023, LA_LIM = 1023;
 
@@ -216,13 +249,26 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     int16_t *Le1 = (int16_t *)(bB2 + NT);                           // extrinsics of the two constituent decoders
     int16_t *Le2 = Le1 + NP;
     uint16_t *s_piT = (uint16_t *)(Le2 + NP);                       // interleaver and its CSR inverse, staged once per block
-    uint16_t *s_cs = s_piT + NP, *s_cp = s_cs + (NP + 2);
-    int8_t *Ls = (int8_t *)(s_cp + NP + 2);
+    // standalone decoder: one contiguous image of the global table blob (bulk copy); fused receive kernel: the tables are staged by the
+    // threads after the input phase (measured faster there: the copy engine's transfer competes with the gather and its completion is
+    // waited for at a barrier, profiles/), with the tighter NP+2 spacing
+    constexpr int CSP = FUSED ? 2 : 8;
+    uint16_t *s_cs = s_piT + NP, *s_cp = s_cs + (NP + CSP);
+    int8_t *Ls = (int8_t *)(s_cp + NP + CSP);
     int8_t *Lp1 = Ls + NP, *Lp2 = Lp1 + NP;
     __shared__ float s_red[32];
     __shared__ int s_tail[12];
 
     const int cb = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    constexpr uint32_t TAB_BYTES = (3 * NP + 16) * 2;
+    uint64_t *s_bar = table_barrier<FUSED>();
+    if constexpr (!FUSED) {
+        if (tid == 0) {
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, TAB_BYTES);
+            bulk_copy_g2s(s_piT, piT, TAB_BYTES, s_bar);         // piT | csr_start (NP+8) | csr_pos (NP+8), laid out like this in HBM
+        }
+    }
     const float *d = llr + (size_t)cb * 3 * (K + 4);
     // ---- input: thread w owns steps 16w..16w+15 = 48 consecutive floats (192 B, 16-byte aligned), read once as float4.
     // max |d| over all 3(K+4) inputs (sentinel -> 0) first, then quantisation straight from registers.
@@ -330,11 +376,16 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
     }
     if (tid < 12) s_tail[tid] = qf(tail_v, maxv);  // s_tail[3*r + x] = q(d_x[K+r])
     for (int i = tid; i < NT * 4; i += nt) bA1[i] = make_uint4(0, 0, 0, 0);  // bA1,bB1,bA2,bB2 are contiguous
-    for (int p = tid; p < NP; p += nt) s_piT[p] = piT[p];
-    for (int j = tid; j <= NP; j += nt) s_cs[j] = csr_start[j];
-    for (int j = tid; j < NP; j += nt) s_cp[j] = j < K ? csr_pos[j] : (uint16_t)0;
-    if (tid < 2) s_cp[NP + tid] = 0;                                        // s_cp[t0+1], s_cp[t0+2] are read unconditionally
-    __syncthreads();
+    if constexpr (FUSED) {
+        for (int p = tid; p < NP; p += nt) s_piT[p] = piT[p];
+        for (int j = tid; j <= NP; j += nt) s_cs[j] = csr_start[j];
+        for (int j = tid; j < NP; j += nt) s_cp[j] = j < K ? csr_pos[j] : (uint16_t)0;
+        if (tid < 2) s_cp[NP + tid] = 0;                                    // s_cp[t0+1], s_cp[t0+2] are read unconditionally
+        __syncthreads();
+    } else {
+        __syncthreads();
+        mbar_wait(s_bar, 0);                                            // tables have landed (zero padding of csr_pos comes with the blob)
+    }
 
     Pass P1, P2;
     P1.Ls = Ls; P1.LeSrc = Le2; P1.piT = s_piT; P1.cs = s_cs; P1.cp = s_cp; P1.Lp = Lp1; P1.LeOut = Le1; P1.st = st; P1.bA = bA1; P1.bB = bB1;
@@ -442,16 +493,20 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
             for (int q = 0; q < NP; q++) cs[q + 1] = (uint16_t)(cs[q] + cnt[q]);
             std::vector<int> fill(cs.begin(), cs.end() - 1);
             for (int i = 0; i < K; i++) cp[fill[pos(pi[i])]++] = pos(i);   // increasing i inside each list
-            LTE_CUDA_OK(ctx, cudaMalloc(&mt.piT, NP * 2));
-            LTE_CUDA_OK(ctx, cudaMalloc(&mt.csr_start, (NP + 1) * 2));
-            LTE_CUDA_OK(ctx, cudaMalloc(&mt.csr_pos, K * 2));
-            LTE_CUDA_OK(ctx, cudaMemcpy(mt.piT, piT.data(), NP * 2, cudaMemcpyHostToDevice));
-            LTE_CUDA_OK(ctx, cudaMemcpy(mt.csr_start, cs.data(), (NP + 1) * 2, cudaMemcpyHostToDevice));
-            LTE_CUDA_OK(ctx, cudaMemcpy(mt.csr_pos, cp.data(), K * 2, cudaMemcpyHostToDevice));
+            // one blob, copied into shared memory by a single bulk copy: piT [NP] | csr_start [NP+8] | csr_pos [NP+8], zero padded
+            std::vector<uint16_t> blob((size_t)3 * NP + 16, 0);
+            memcpy(blob.data(), piT.data(), (size_t)NP * 2);
+            memcpy(blob.data() + NP, cs.data(), (size_t)(NP + 1) * 2);
+            for (int j = NP + 1; j < NP + 8; j++) blob[NP + j] = cs[NP];
+            memcpy(blob.data() + 2 * NP + 8, cp.data(), (size_t)K * 2);
+            LTE_CUDA_OK(ctx, cudaMalloc(&mt.piT, blob.size() * 2));
+            LTE_CUDA_OK(ctx, cudaMemcpy(mt.piT, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice));
+            mt.csr_start = mt.piT + NP;
+            mt.csr_pos = mt.csr_start + NP + 8;
             ctx->mlm[K] = mt;
         } else mt = it->second;
     }
-    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)2 * NP * 2 + (size_t)(3 * NP + 4) * 2 + (size_t)3 * NP;
+    const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)2 * NP * 2 + (size_t)(3 * NP + (fused ? 4 : 16)) * 2 + (size_t)3 * NP;
     const int threads = ((nw + 31) / 32) * 32;
     FusedParams none;
     memset(&none, 0, sizeof(none));
