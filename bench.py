@@ -114,7 +114,7 @@ def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_s
         refo.lib()
     idx = list(range(n_sample))
     chunks = [idx[t::threads] for t in range(threads)]
-    ok_all = [True] * threads
+    fails = [0] * threads
 
     def work(t):
         if use_ref:
@@ -130,13 +130,13 @@ def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_s
                 for a, al in enumerate(ALLOCS):
                     err, bits = phy.pdsch_decode_big(sf, CFI, CELL, al["mod"], al["prb"], al["tbs"], al["rnti"])
                     if err != 0 or not np.array_equal(bits, tb_seg[b % seg, a]):
-                        ok_all[t] = False
+                        fails[t] += 1
             else:
                 rx_re, rx_im, ce_re, ce_im = port.get_dl_subframe_and_ce(iq_f32_i, iq_f32_q, FS_IDX, N_RB, fstart, sn, CELL, 1)
                 for a, al in enumerate(ALLOCS):
                     rc, bits = port.pdsch_decode(rx_re, rx_im, ce_re[0], ce_im[0], N_RB, CELL, sn, CFI, al["mod"], al["prb"], al["tbs"], al["rnti"])
                     if rc != 0 or not np.array_equal(bits, tb_seg[b % seg, a]):
-                        ok_all[t] = False
+                        fails[t] += 1
 
     barrier = threading.Barrier(threads + 1)
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -147,7 +147,8 @@ def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_s
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    return n_sample / dt, kind, all(ok_all), dt
+    n_tb = n_sample * len(ALLOCS)
+    return n_sample / dt, kind, "%d of %d transport blocks decoded correctly by the reference's decoder" % (n_tb - sum(fails), n_tb), dt
 
 
 def cpu_stage_times(iq_f32_i, iq_f32_q, start, subfr, n_sample):
@@ -197,7 +198,7 @@ def run_reference(args, rank, world):
            "config": {"workload": WORKLOAD, "subframes_per_step": n_sample, "turbo": "reference turbo_decode (3 SISO Viterbi passes; the reference has no iterative decoder)",
                       "fft": "single-precision radix-4 Stockham stand-in for FFTW3f (oracle/fftw3_shim)"},
            "cpu_baseline": {"value": value, "unit": "subframes/s", "cores": threads, "kind": kind,
-                            "sample": f"{n_sample} subframes per step x {len(rates)} steps, one LIBLTE_PHY_STRUCT per thread, all CRC ok: {ok}"},
+                            "sample": f"{n_sample} subframes per step x {len(rates)} steps, one LIBLTE_PHY_STRUCT per thread, {ok}"},
            "e2e": {"value": value, "unit": "subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -415,7 +416,7 @@ def main():
         if r1 > r:
             r, okc, dt, threads, n_sample = r1, ok1, dt1, 1, 16
         cpu = {"value": round(r, 2), "unit": "subframes/s", "cores": threads, "kind": kind,
-               "sample": f"{n_sample} subframes of the same workload over {threads} threads ({dt:.2f} s wall), reference turbo_decode, FFT = oracle/fftw3_shim; all CRC ok: {okc}",
+               "sample": f"{n_sample} subframes of the same workload over {threads} threads ({dt:.2f} s wall), reference turbo_decode, FFT = oracle/fftw3_shim; {okc}",
                "value_1core": round(r1, 2), "all_threads": all_threads, "stage_ms_per_subframe_1core": stages_1core}
 
     if rank == 0:
