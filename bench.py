@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-pass", action="store_true", help="stop after the device-resident timed steps (for the ncu launch list of the step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -328,6 +329,13 @@ def main():
     l0 = ctx.launches
     ms = timed(step_resident, args.steps)
     launches = ctx.launches - l0
+    if args.profile_pass:
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_pass": True, "ms_per_step": round(ms / args.steps, 4), "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- timed: end to end through the host-pointer C-ABI call
     for _ in range(3):
         step_e2e()
