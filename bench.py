@@ -401,7 +401,7 @@ def main():
                            ("pdsch_receive_fused(demod+unmatch+turbo+crc, all allocs)" if args.turbo_mode else "pdsch_receive_staged(all allocs)", t_fused, b_fused)):
             stages[name] = {"ms": round(t, 4), "alg_GB": round(b * GB, 4), "GBps": round(b * GB / (t * 1e-3), 1), "frac_hbm": round(b * GB / (t * 1e-3) / hbm_peak, 4)}
         # dominant kernel of the step: the fused receive kernel (mode B) / the SISO kernels (mode A).  `traffic` = dram bytes per
-        # launch from the committed ncu --set full capture (profiles/r1_fused_ncu_summary.json: 957.6 MB read + 95.0 MB written for
+        # launch from the committed ncu --set full capture (profiles/r1_chain_ncu_summary.json: 957.6 MB read + 95.0 MB written for
         # 16,000 transport blocks = 65.8 KB each)
         dom_t, dom_b = (t_fused, b_fused) if args.turbo_mode else (t_ta, b_turbo)
         roof = {"bound": "hbm", "kernel": "turbo_mlm_kernel<16,true> (fused PDSCH receive)" if args.turbo_mode else "turbo_ref_siso (+prep/mid/final)",
