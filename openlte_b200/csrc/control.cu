@@ -246,14 +246,16 @@ pdcch_decode_kernel(const float2 *__restrict__ grid, const float2 *__restrict__ 
     }
     const int N_symbs = cfi + (P.N_rb_dl <= 10 ? 1 : 0);
     // the 16 CCEs of the common search space: gather, zero forcing, QPSK demap, descramble with c(subframe, cell)
-    const int32_t *re_of = T.cce_re + (N_symbs - 1) * 576;
+    // reserved CFI 4 on a <= 10 RB carrier would mean five control symbols: no CCE map exists, every element counts as missing (as in the oracle)
+    const bool no_map = N_symbs > 4;
+    const int32_t *re_of = T.cce_re + (no_map ? 0 : (N_symbs - 1) * 576);
     const uint8_t *c = T.c_pdcch + sn * 1152;
     for (int t = tid; t < 1152; t += blockDim.x) {
         // t < 576: aggregation level 4, candidate t/144, element t%144; else level 8, candidate (t-576)/288
         const int cand = t < 576 ? t / 144 : 4 + (t - 576) / 288;
         const int j = t < 576 ? t % 144 : (t - 576) % 288;
         const int e = t < 576 ? t : t - 576;            // element of the 16-CCE space
-        const int re = re_of[e];
+        const int re = no_map ? -1 : re_of[e];
         int b0 = 0, b1 = 0;                             // CCE beyond the control region: soft bits 0 (see oracle/port/control.cc)
         if (re >= 0) {
             float xr, xi;

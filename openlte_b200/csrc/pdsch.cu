@@ -248,6 +248,7 @@ extern "C" int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *d_grid, 
                                          int soft_stride, int *n_bits_out, void *stream)
 {
     if (!ctx || !d_grid || !d_ce || !subfr_num || !alloc || !d_soft || n_sf < 1) return LTEB200_ERR_ARGS;
+    if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
     int *d_sn = nullptr;
@@ -267,6 +268,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
                                           int turbo_mode, int n_iter, uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
 {
     if (!ctx || !d_grid || !d_ce || !subfr_num || !allocs || !d_tb_bits || !d_crc_ok || n_sf < 1 || n_alloc < 1) return LTEB200_ERR_ARGS;
+    if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     cudaStream_t stream = (cudaStream_t)stream_;
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); return LTEB200_ERR_ARGS; }

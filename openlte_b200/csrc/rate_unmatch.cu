@@ -131,6 +131,7 @@ extern "C" int lteb200_rate_unmatch_turbo_batch(lteb200_ctx *ctx, const float *d
                                                 float *d_out, void *stream)
 {
     if (!ctx || !d_e || !d_out || n_cb < 0 || e_stride < E) return LTEB200_ERR_ARGS;
+    if (n_cb > 65535) { lteb200_set_error(ctx, "at most 65535 code blocks per call (split the batch)"); return LTEB200_ERR_ARGS; }
     if (n_cb == 0) return LTEB200_OK;
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     RateUnmatchMap m;

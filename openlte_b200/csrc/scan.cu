@@ -29,6 +29,7 @@ extern "C" int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_
                                      lteb200_scan_result *results, uint8_t *tb_bits, long long tb_capacity, long long *tb_used, void *stream_)
 {
     if (!ctx || !d_iq || !start_idx || !subfr_num || !results || !tb_bits || !tb_used || n_sf < 1 || tb_capacity < 0) return LTEB200_ERR_ARGS;
+    if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     cudaStream_t stream = (cudaStream_t)stream_;
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     *tb_used = 0;

@@ -180,6 +180,7 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
         (!d_grid && !d_iq))
         return LTEB200_ERR_ARGS;
     if (N_ant != 1) { lteb200_set_error(ctx, "dl_transmit: one antenna port only"); return LTEB200_ERR_UNSUPPORTED; }
+    if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     const int N = 128 << fs_idx, nsc = 12 * N_rb_dl;
     if (nsc >= N) { lteb200_set_error(ctx, "dl_transmit: N_rb_dl does not fit the sample rate"); return LTEB200_ERR_ARGS; }
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
