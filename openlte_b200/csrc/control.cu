@@ -242,6 +242,7 @@ pdcch_decode_kernel(const float2 *__restrict__ grid, const float2 *__restrict__ 
     if (cfi == 0) {
         if (tid == 0) { o->cfi = 0; o->N_symbs = 0; }
         if (tid < N_HYP) { o->found[tid] = 0; o->rnti[tid] = 0; }
+        o->bits[warp][lane] = 0;                        // deterministic output for subframes without a control region
         return;
     }
     const int N_symbs = cfi + (P.N_rb_dl <= 10 ? 1 : 0);
