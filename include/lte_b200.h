@@ -206,6 +206,9 @@ typedef struct {
 } lteb200_dci;
 int lteb200_pdcch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
                                float phich_res, const int *subfr_num, int n_sf, lteb200_pdcch_raw *d_out, void *stream);
+/* HOST: where the common search space sits in the grid: out576[36*c + j] = symbol*(12*N_rb_dl) + subcarrier of element j of CCE c < 16
+ * (REG walk, cyclic shift, REG de-interleaver and CCE assembly of liblte_phy.cc:4591-4838 folded into one table), -1 = no such CCE. */
+int lteb200_pdcch_cce_map(int N_rb_dl, int N_id_cell, int N_ant, int N_symbs, float phich_res, int32_t *out576);
 /* HOST: dci_1a_unpack / dci_1c_unpack (liblte_phy.cc:13273, 13400) over one subframe's raw results, in the reference's order,
  * at most 6 allocations; return value mirrors the reference's (see control.cu). */
 int lteb200_pdcch_unpack(const lteb200_pdcch_raw *raw, int N_rb_dl, int N_ant, lteb200_dci *allocs, int *N_alloc);

@@ -562,6 +562,17 @@ int unpack_1c(const uint8_t *bits, int rnti, int N_rb_dl, int N_ant, lteb200_dci
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ C ABI
+// HOST utility: resource elements of the first 16 CCEs (the common search space), element j of CCE c at out[36*c + j] as
+// symbol*(12*N_rb_dl) + subcarrier, -1 where the control region has no such CCE.  What the decode kernel gathers from; exposed so that
+// the mapping can be checked without a device (tests/test_control_oracle.py) and reused by signal generators.
+extern "C" int lteb200_pdcch_cce_map(int N_rb_dl, int N_id_cell, int N_ant, int N_symbs, float phich_res, int32_t *out576)
+{
+    if (!out576 || N_rb_dl < 6 || N_rb_dl > 110 || N_id_cell < 0 || N_id_cell > 503 || N_symbs < 1 || N_symbs > 4 || !(N_ant == 1 || N_ant == 2 || N_ant == 4))
+        return LTEB200_ERR_ARGS;
+    build_cce_map(N_rb_dl, N_id_cell, N_ant, N_symbs, phich_res, 12 * N_rb_dl, out576);
+    return LTEB200_OK;
+}
+
 extern "C" int lteb200_bch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int n,
                                         lteb200_bch_result *d_out, void *stream)
 {

@@ -73,3 +73,62 @@ def test_pdcch_of_the_shipped_capture(port):
     assert r["err"] == 0 and r["cfi"] == int(g["cfi"]) and len(r["allocs"]) >= 1
     a = r["allocs"][0]
     assert (a["rnti"], a["tbs"], a["mod_type"], a["rv_idx"], a["prb"]) == (int(g["rnti"]), int(g["tbs"]), int(g["mod"]), int(g["rv"]), g["prb"].tolist())
+
+
+def test_product_cce_map_equals_oracle_for_every_bandwidth(port):
+    """The table the PDCCH kernel gathers from (host code inside libopenlte_b200.so, callable without a device) against the oracle's
+    restatement of the reference's REG walk / shift / de-interleaver, for all six bandwidths, 1-4 control symbols, three PHICH
+    resources and a spread of cell identities; plus the structural property: no resource element is used twice and none is a CRS,
+    PCFICH or PHICH position."""
+    import ctypes as C
+    import openlte_b200
+    lib = openlte_b200.load()
+    out = np.zeros(576, np.int32)
+    n_checked = 0
+    for nrb in (6, 15, 25, 50, 75, 100):
+        nsc = 12 * nrb
+        for cell in (0, 1, 2, 5, 77, 150, 301, 503):
+            for pres in (1 / 6, 1.0, 2.0):
+                for ns in (1, 2, 3, 4):
+                    want, n_reg = port.pdcch_cce_map(nrb, cell, 1, ns, pres)
+                    assert lib.pdcch_cce_map(nrb, cell, 1, ns, C.c_float(pres), out.ctypes.data_as(C.c_void_p)) == 0
+                    n_cce = want.shape[0]
+                    got = out.reshape(16, 36)
+                    for c in range(16):
+                        if c < n_cce:
+                            w = (want[c] // 1200) * nsc + (want[c] % 1200)          # the oracle addresses rows of 1200 subcarriers
+                            assert np.array_equal(got[c], w), (nrb, cell, pres, ns, c)
+                        else:
+                            assert (got[c] == -1).all()
+                    used = got[:min(n_cce, 16)].reshape(-1)
+                    assert used.size == np.unique(used).size
+                    sym, k = used // nsc, used % nsc
+                    assert (sym < ns).all()
+                    assert not ((sym == 0) & (k % 3 == cell % 3)).any()              # CRS positions of symbol 0 (both ports' offsets)
+                    n_checked += 1
+    assert n_checked == 6 * 8 * 3 * 4
+
+
+def test_product_dci_unpack_against_reference_fixtures():
+    """lteb200_pdcch_unpack is host code: the reference's dci_1a_unpack / dci_1c_unpack results on random payloads (fixtures) must come
+    back from it field for field, without a device."""
+    import ctypes as C
+    import openlte_b200
+    from openlte_b200.lib import PdcchRaw, Dci
+    lib = openlte_b200.load()
+    g = gold("control_pieces_ref.npz")
+    n_ok = 0
+    for row in g["dci_rows"]:
+        N, fmt, rnti, err = [int(x) for x in row[:4]]
+        raw = PdcchRaw(); raw.cfi = 2; raw.N_symbs = 2
+        slot = fmt                                   # candidate 0, format 1A -> slot 0, 1C -> slot 1
+        raw.found[slot] = 1; raw.rnti[slot] = rnti
+        for i in range(32):
+            raw.bits[slot][i] = int(row[4 + i])
+        allocs = (Dci * 6)(); n = C.c_int(0)
+        rc = lib.pdcch_unpack(C.byref(raw), N, 1, allocs, C.byref(n))
+        assert (rc != 0) == (err != 0), (N, fmt, rc, err)
+        if err == 0:
+            assert n.value == 1 and np.array_equal(alloc_row(allocs[0].as_dict()), row[36:]), (N, fmt)
+            n_ok += 1
+    assert n_ok > 100
