@@ -280,8 +280,11 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
     }
     // ---- fused path: one kernel per group of allocations with equal K does demod + unmatch + decode + CRC per transport block
-    bool fusable = turbo_mode == LTEB200_TURBO_MAXLOGMAP && N_ant == 1 && !getenv("LTEB200_NO_FUSE");
+    bool fusable = turbo_mode == LTEB200_TURBO_MAXLOGMAP && !getenv("LTEB200_NO_FUSE");
     for (int a = 0; a < n_alloc && fusable; a++) {
+        // transmit diversity works on whole groups of N_ant resource elements: ragged tails stay on the staged path (which drops the odd
+        // element of a 2-port allocation like the reference and refuses the 4-port case)
+        for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant != 0) fusable = false;
         // the fused kernel stages an allocation's soft bits in the shared memory of its forward-metric store: 64 floats per window column
         const int nw = (T[a].K + 15) / 16, NT = nw <= 64 ? 64 : (nw <= 128 ? 128 : 384);
         if (T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;
@@ -296,6 +299,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
             FusedParams fp;
             memset(&fp, 0, sizeof(fp));
             fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.crc_tab = crc_tab;
+            fp.N_ant = N_ant;
             fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
             int e = a;
             while (e < n_alloc && e - a < 8 && T[e].K == T[a].K) {

@@ -101,5 +101,6 @@ struct FusedParams {
     uint8_t *tb_out;
     int32_t *crc_ok;
     int nsc, n_sf, n_alloc_total, tb_stride, n_al;
+    int N_ant;                // 1: zero forcing; 2 / 4: transmit-diversity combining of groups of N_ant resource elements
     FusedAlloc al[8];
 };

@@ -284,9 +284,30 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
         const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
         const int M = A.M[cls], E = M * A.Qm;
         float *soft = reinterpret_cast<float *>(st);                       // <= 20,700 floats, the metric store is idle now
-        const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * 14 * fp.nsc;
+        const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
         const int *ix = A.re_idx + cls * A.idx_stride;
         const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
+        if (fp.N_ant != 1) {
+            // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
+            const size_t ps = (size_t)14 * fp.nsc;
+            auto emit = [&](int r, float2 x) {
+                int b[6];
+                demap_bits(x.x, x.y, A.mod, b);
+                for (int t = 0; t < A.Qm; t++) soft[r * A.Qm + t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)cs[r * A.Qm + t]));
+            };
+            for (int r = tid * fp.N_ant; r < M; r += nt * fp.N_ant) {
+                if (fp.N_ant == 2) {
+                    float2 x0, x1;
+                    sfbc2(gr[ix[r]], gr[ix[r + 1]], ch[ix[r]], ch[ps + ix[r]], x0, x1);
+                    emit(r, x0); emit(r + 1, x1);
+                } else {
+                    const float2 y[4] = {gr[ix[r]], gr[ix[r + 1]], gr[ix[r + 2]], gr[ix[r + 3]]};
+                    float2 x[4];
+                    sfbc4(y, ch[ix[r]], ch[ps + ix[r + 2]], ch[2 * ps + ix[r]], ch[3 * ps + ix[r + 2]], x);
+                    for (int q = 0; q < 4; q++) emit(r + q, x[q]);
+                }
+            }
+        } else {
         // every thread handles up to RE_IT resource elements; indices, grid and estimate values are all fetched before the
         // arithmetic starts, so the global-memory latency is paid once, not per element
         constexpr int RE_IT = 4;
@@ -308,6 +329,7 @@ turbo_mlm_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_
                     for (int t = 0; t < A.Qm; t++) soft[r * A.Qm + t] = __fmul_rn((float)b[t], (float)(1 - 2 * (int)cs[r * A.Qm + t]));
                 }
             }
+        }
         }
         __syncthreads();
         // rate unmatching (liblte_phy.cc:11403-11415): first visit assigns, repeats are added in visiting order

@@ -326,3 +326,31 @@ def test_north_star_load_punctured_blocks(ctx):
     for a in range(12):
         assert np.array_equal(out[1][0][:, a], tx["tb"][a])
     assert not out[0][1].any(), "the reference-exact decoder is expected to fail on punctured code words, as the reference does"
+
+
+@pytest.mark.parametrize("name", ["loop_2ant_16qam_c21_sf2.npz", "loop_4ant_qpsk_10mhz_c400_sf5.npz", "loop_2ant_64qam_c5_sf7.npz"])
+def test_fused_receive_with_transmit_diversity_equals_staged(ctx, name):
+    """2- and 4-port allocations (transmit-diversity combining inside the fused kernel) against the staged kernels, on the
+    reference-generated loopback fixtures: same CRC verdict, same transport block."""
+    import torch
+    case = _loopback_case(name)
+    n_tx = int(case["N_ant_tx"])
+    _, _, grid, ce = gpu_front(ctx, case)
+    al = Alloc.make(int(case["mod"]), [int(x) for x in case["prb"]], int(case["tbs"]), int(case["rnti"]))
+    sn = np.array([int(case["subfr"])], np.int32)
+    res = {}
+    for fuse in (True, False):
+        if fuse:
+            os.environ.pop("LTEB200_NO_FUSE", None)
+        else:
+            os.environ["LTEB200_NO_FUSE"] = "1"
+        tb = torch.zeros((1, 1, int(case["tbs"])), dtype=torch.uint8, device="cuda"); ok = torch.zeros((1, 1), dtype=torch.int32, device="cuda")
+        l0 = ctx.launches
+        ctx.check(ctx.lib.pdsch_decode_batch(ctx.h, dptr(grid), dptr(ce), int(case["N_rb_dl"]), int(case["N_id_cell"]), n_tx, sn.ctypes.data_as(C.c_void_p), 1,
+                                             int(case["cfi"]), C.byref(al), 1, 1, 8, dptr(tb), int(case["tbs"]), dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        res[fuse] = (tb.cpu().numpy()[0, 0], int(ok.item()), ctx.launches - l0)
+    os.environ.pop("LTEB200_NO_FUSE", None)
+    assert res[True][2] < res[False][2], "the fused path was not taken"
+    assert res[True][1] == res[False][1] == 1
+    assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][0], case["tb"])
