@@ -587,8 +587,7 @@ extern "C" int lteb200_bch_decode_batch(lteb200_ctx *ctx, const float *d_grid, c
     if (rc) return rc;
     BchParams P{12 * N_rb_dl, 6 * N_rb_dl - 36, N_id_cell % 3};
     const size_t smem = sizeof(int) * (N_HYP * 41 * 64 + N_HYP * 120) + sizeof(float2) * 5 * 240 + sizeof(int16_t) * 3 * 480 + N_HYP * 40;
-    static bool attr = false;
-    if (!attr) { LTE_CUDA_OK(ctx, cudaFuncSetAttribute(bch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(bch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every call
     bch_decode_kernel<<<n, 32 * N_HYP, smem, (cudaStream_t)stream>>>((const float2 *)d_grid, (const float2 *)d_ce, c, order, P, d_out);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
@@ -618,8 +617,7 @@ extern "C" int lteb200_pdcch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
     if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     PdcchParams P{12 * N_rb_dl, N_rb_dl};
     const size_t smem = sizeof(int) * (N_HYP * PM_STRIDE + N_HYP * 3 * CC_MAX_N) + sizeof(int16_t) * 6 * 576 + N_HYP * CC_MAX_N;
-    static bool attr = false;
-    if (!attr) { LTE_CUDA_OK(ctx, cudaFuncSetAttribute(pdcch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(pdcch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pdcch_decode_kernel<<<n_sf, 32 * N_HYP, smem, stream>>>((const float2 *)d_grid, (const float2 *)d_ce, d_sn, T, P, d_out);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());

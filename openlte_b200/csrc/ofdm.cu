@@ -86,9 +86,6 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 mulmj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
 
 template <int R> struct Dft;
-template <> struct Dft<2> {
-    __device__ __forceinline__ static void run(float2 *x) { const float2 a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
-};
 template <> struct Dft<4> {
     __device__ __forceinline__ static void run(float2 *x)
     {
