@@ -18,3 +18,11 @@ int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
 int get_twiddles(lteb200_ctx *ctx, int N, float2 **out);                 // e^{-2 pi i k/N}, k < N (ofdm.cu)
 int get_crs_table(lteb200_ctx *ctx, int N_id_cell, float2 **out);        // [20][3][220] (chanest.cu)
 int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv, RateUnmatchMap *out);
+
+// Size class of the max-log-MAP kernel for a code block of K bits: row stride (= threads per CTA) of its shared-memory arrays.  Shared memory
+// scales with it (about 528 bytes per unit), so 64 / 128 / 192 leave room for 6 / 3 / 2 CTAs per SM and 384 for one.
+static inline int mlm_size_class(int K)
+{
+    const int nw = (K + 15) / 16;
+    return nw <= 64 ? 64 : (nw <= 128 ? 128 : (nw <= 192 ? 192 : 384));
+}

@@ -286,7 +286,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         // element of a 2-port allocation like the reference and refuses the 4-port case)
         for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant != 0) fusable = false;
         // the fused kernel stages an allocation's soft bits in the shared memory of its forward-metric store: 64 floats per window column
-        const int nw = (T[a].K + 15) / 16, NT = nw <= 64 ? 64 : (nw <= 128 ? 128 : 384);
+        const int NT = mlm_size_class(T[a].K);
         if (T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;
     }
     if (fusable) {

@@ -14,7 +14,7 @@
 // iteration, so all K/32 windows of a block advance in parallel without warm-up recursions.  Shared-memory
 // arrays use a window-transposed layout pos(k) = (k mod 32)*nw + k/32 so that at every step the threads of a
 // warp touch consecutive addresses (conflict free).  No tensor cores (no contraction on this path).
-#include "common.cuh"
+#include "internal.h"
 #include "pdsch_dev.cuh"
 
 #ifndef MLM_WIN
@@ -500,7 +500,7 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
     constexpr int WIN = MLM_WIN;
     const int nw = (K + WIN - 1) / WIN;
     // size class: shared memory (and therefore blocks per SM) scales with the block size
-    const int NT = nw <= 64 ? 64 : (nw <= 128 ? 128 : 6144 / WIN), NP = WIN * NT;
+    const int NT = mlm_size_class(K), NP = WIN * NT;
     MlmTables mt;
     {
         auto it = ctx->mlm.find(K);
@@ -538,8 +538,8 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
         LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm_kernel<WIN, NT_, FUSED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         turbo_mlm_kernel<WIN, NT_, FUSED_><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, mt.piT, mt.csr_start, mt.csr_pos, d_bits, fp); \
     } while (0)
-    if (fused) { if (NT == 64) MLM_LAUNCH(64, true); else if (NT == 128) MLM_LAUNCH(128, true); else MLM_LAUNCH(6144 / WIN, true); }
-    else       { if (NT == 64) MLM_LAUNCH(64, false); else if (NT == 128) MLM_LAUNCH(128, false); else MLM_LAUNCH(6144 / WIN, false); }
+    if (fused) { if (NT == 64) MLM_LAUNCH(64, true); else if (NT == 128) MLM_LAUNCH(128, true); else if (NT == 192) MLM_LAUNCH(192, true); else MLM_LAUNCH(384, true); }
+    else       { if (NT == 64) MLM_LAUNCH(64, false); else if (NT == 128) MLM_LAUNCH(128, false); else if (NT == 192) MLM_LAUNCH(192, false); else MLM_LAUNCH(384, false); }
 #undef MLM_LAUNCH
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
