@@ -32,6 +32,7 @@ ALLOCS = [dict(mod=3, prb=list(range(25 * a, 25 * a + 25)), tbs=6120, rnti=0x100
 K_CB, TBS = 6144, 6120
 SEG = 40                      # distinct synthetic subframes; the stream tiles this segment (numbering stays consecutive)
 WORKLOAD = "dl_chain_20MHz_100RB_64QAM_4x25PRB_TBS6120_K6144_cfi2_1port"
+METRIC = "DL subframes/sec (20MHz,64QAM,K=6144,8 turbo iters) @1/2/4/8 GPU vs CPU ref"      # BASELINE.json, both arms print exactly this
 
 
 def make_stream(n_sf, seed):
@@ -104,39 +105,32 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_seg, seg=SEG):
-    """Times the reference's own CPU implementation of the same chain on `n_sample` subframes over `threads` host
-    threads (one LIBLTE_PHY_STRUCT per thread).  Returns (subframes/s, kind, all_crc_ok)."""
+    """Times the reference's own CPU implementation of the same chain on `n_sample` subframes over `threads` host threads, one
+    LIBLTE_PHY_STRUCT per thread.  With oracle/_ref present this is a native std::thread pool inside the oracle library
+    (oracle/ref_wrap.cc: ref_chain_pool -- structs and FFT plans created serially before the clock starts, no allocation per transport
+    block); without it, the oracle port driven from Python threads.  Returns dict(rate, kind, note, wall_s, front_s, pdsch_s, build)."""
     from oracle import ref as refo, port
-    use_ref = refo.available()
-    kind = "reference" if use_ref else "port"
+    n_tb = n_sample * len(ALLOCS)
+    if refo.available():
+        r = refo.chain_pool(threads, iq_f32_i, iq_f32_q, start[:n_sample], subfr[:n_sample], ALLOCS, CELL, CFI, N_RB, 30.72,
+                            want_tb=tb_seg, seg=seg)
+        return dict(rate=n_sample / r["seconds"], kind="reference", wall_s=r["seconds"], front_s=r["front_s"], pdsch_s=r["pdsch_s"], build=r["flags"],
+                    note="%d of %d transport blocks decoded correctly by the reference's decoder" % (n_tb - r["fails"], n_tb))
     port.lib()
-    if use_ref:
-        refo.lib()
     idx = list(range(n_sample))
     chunks = [idx[t::threads] for t in range(threads)]
     fails = [0] * threads
 
     def work(t):
-        if use_ref:
-            phy = refo.RefPhy(fs=30.72, N_id_cell=CELL, N_ant=1, N_rb_dl=N_RB)   # struct + FFT plans exist before the clock starts
-            sf = refo.Subframe()
         barrier.wait()
         for b in chunks[t]:
             sn = int(subfr[b])
-            # liblte_phy_get_dl_subframe_and_ce addresses the subframe as frame_start_idx + subfr_num*N (uint32 arithmetic)
             fstart = (int(start[b]) - sn * SF_SAMPS) & 0xFFFFFFFF
-            if use_ref:
-                phy.get_dl_subframe_and_ce(iq_f32_i, iq_f32_q, fstart, sn, CELL, 1, sf)
-                for a, al in enumerate(ALLOCS):
-                    err, bits = phy.pdsch_decode_big(sf, CFI, CELL, al["mod"], al["prb"], al["tbs"], al["rnti"])
-                    if err != 0 or not np.array_equal(bits, tb_seg[b % seg, a]):
-                        fails[t] += 1
-            else:
-                rx_re, rx_im, ce_re, ce_im = port.get_dl_subframe_and_ce(iq_f32_i, iq_f32_q, FS_IDX, N_RB, fstart, sn, CELL, 1)
-                for a, al in enumerate(ALLOCS):
-                    rc, bits = port.pdsch_decode(rx_re, rx_im, ce_re[0], ce_im[0], N_RB, CELL, sn, CFI, al["mod"], al["prb"], al["tbs"], al["rnti"])
-                    if rc != 0 or not np.array_equal(bits, tb_seg[b % seg, a]):
-                        fails[t] += 1
+            rx_re, rx_im, ce_re, ce_im = port.get_dl_subframe_and_ce(iq_f32_i, iq_f32_q, FS_IDX, N_RB, fstart, sn, CELL, 1)
+            for a, al in enumerate(ALLOCS):
+                rc, bits = port.pdsch_decode(rx_re, rx_im, ce_re[0], ce_im[0], N_RB, CELL, sn, CFI, al["mod"], al["prb"], al["tbs"], al["rnti"])
+                if rc != 0 or not np.array_equal(bits, tb_seg[b % seg, a]):
+                    fails[t] += 1
 
     barrier = threading.Barrier(threads + 1)
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -147,59 +141,79 @@ def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_s
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    n_tb = n_sample * len(ALLOCS)
-    return n_sample / dt, kind, "%d of %d transport blocks decoded correctly by the reference's decoder" % (n_tb - sum(fails), n_tb), dt
+    return dict(rate=n_sample / dt, kind="port", wall_s=dt, front_s=None, pdsch_s=None, build="oracle port, Python threads",
+                note="%d of %d transport blocks decoded correctly by the port" % (n_tb - sum(fails), n_tb))
 
 
-def cpu_stage_times(iq_f32_i, iq_f32_q, start, subfr, n_sample):
-    """One host thread, the reference's own functions timed one by one (ms per subframe): SURVEY 8d 'wall-clock around each stage'."""
-    from oracle import ref as refo
-    if not refo.available():
-        return None
-    phy = refo.RefPhy(fs=30.72, N_id_cell=CELL, N_ant=1, N_rb_dl=N_RB)
-    sf = refo.Subframe()
-    t_front = t_pdsch = 0.0
-    for b in range(n_sample):
-        sn = int(subfr[b]); fstart = (int(start[b]) - sn * SF_SAMPS) & 0xFFFFFFFF
-        t0 = time.perf_counter()
-        phy.get_dl_subframe_and_ce(iq_f32_i, iq_f32_q, fstart, sn, CELL, 1, sf)
-        t1 = time.perf_counter()
-        for al in ALLOCS:
-            phy.pdsch_decode_big(sf, CFI, CELL, al["mod"], al["prb"], al["tbs"], al["rnti"])
-        t2 = time.perf_counter()
-        t_front += t1 - t0; t_pdsch += t2 - t1
-    return {"liblte_phy_get_dl_subframe_and_ce (16 FFTs + channel estimate)": round(1e3 * t_front / n_sample, 3),
-            "liblte_phy_pdsch_channel_decode x %d allocations (demod + rate unmatch + turbo_decode + CRC)" % len(ALLOCS): round(1e3 * t_pdsch / n_sample, 3)}
+def physical_cores():
+    try:
+        seen = set()
+        for d in os.listdir("/sys/devices/system/cpu"):
+            if d.startswith("cpu") and d[3:].isdigit():
+                try:
+                    with open("/sys/devices/system/cpu/%s/topology/thread_siblings_list" % d) as f:
+                        seen.add(f.read().strip())
+                except OSError:
+                    pass
+        if seen:
+            return len(seen)
+    except OSError:
+        pass
+    return os.cpu_count() or 1
+
+
+def best_thread_count(i_f, q_f, start, subfr, tb, seg):
+    """The reference is single-threaded code run as one struct per thread; whether SMT siblings help depends on the host.  Calibrate once
+    (short run each) over {logical CPUs, physical cores} and keep the faster: the CPU arm should be the reference at its best."""
+    logical = os.cpu_count() or 1
+    cands = sorted({logical, min(logical, physical_cores())}, reverse=True)
+    best = None
+    for t in cands:
+        n = max(2 * t, 16)
+        r = cpu_reference_rate(i_f, q_f, start, subfr, n, t, tb, seg)
+        if best is None or r["rate"] > best[1]:
+            best = (t, r["rate"])
+    return best[0], {str(t): None for t in cands}
+
+
+def shared_config(n_sf_step):
+    return {"workload": WORKLOAD, "code_blocks_per_subframe": len(ALLOCS), "K": K_CB, "iq_format": "int8 pairs"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n_sample = args.ref_sample if args.ref_sample else max(threads * 4, 32)
-    iq, start, subfr, tb = make_stream(max(n_sample, SEG), seed=1234)
+    logical = os.cpu_count() or 1
+    n_need = max(8 * logical, 256)
+    iq, start, subfr, tb = make_stream(n_need, seed=1234)
     i_f = np.ascontiguousarray(iq[:, 0].astype(np.float32)); q_f = np.ascontiguousarray(iq[:, 1].astype(np.float32))
-    # the reference is single-threaded code; one struct per thread scales only as far as the host allows: keep the better of
-    # "all host threads" and "one thread" so the CPU arm is never penalised by oversubscribed cores
-    r_all = cpu_reference_rate(i_f, q_f, start, subfr, n_sample, threads, tb)[0]
-    r_one = cpu_reference_rate(i_f, q_f, start, subfr, max(8, n_sample // threads), 1, tb)[0] if threads > 1 else 0.0
-    if r_one > r_all:
-        threads, n_sample = 1, max(8, n_sample // threads)
-    rates = []
+    threads, _ = best_thread_count(i_f, q_f, start, subfr, tb, SEG)
+    one = cpu_reference_rate(i_f, q_f, start, subfr, 16, 1, tb)
+    # a step = a bounded sample of the workload: about 2 s of wall time on this host (at least 4 subframes per thread)
+    probe = cpu_reference_rate(i_f, q_f, start, subfr, max(2 * threads, 16), threads, tb)
+    n_sample = int(min(n_need, max(4 * threads, 32, probe["rate"] * (args.ref_seconds if args.ref_sample == 0 else 0))))
+    if args.ref_sample:
+        n_sample = min(n_need, args.ref_sample)
+    runs = []
     for s in range(args.warmup + args.steps):
-        r, kind, ok, dt = cpu_reference_rate(i_f, q_f, start, subfr, n_sample, threads, tb)
+        r = cpu_reference_rate(i_f, q_f, start, subfr, n_sample, threads, tb)
         if s >= args.warmup:
-            rates.append((r, dt))
-    tot_t = sum(d for _, d in rates)
-    value = n_sample * len(rates) / tot_t
-    out = {"impl": "reference", "metric": "DL subframes/sec (20MHz,64QAM,K=6144) through the reference CPU receive chain", "value": value,
-           "unit": "subframes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / len(rates),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (reference) / int8 soft bits", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "subframes_per_step": n_sample, "turbo": "reference turbo_decode (3 SISO Viterbi passes; the reference has no iterative decoder)",
-                      "fft": "single-precision radix-4 Stockham stand-in for FFTW3f (oracle/fftw3_shim)"},
-           "cpu_baseline": {"value": value, "unit": "subframes/s", "cores": threads, "kind": kind,
-                            "sample": f"{n_sample} subframes per step x {len(rates)} steps, one LIBLTE_PHY_STRUCT per thread, {ok}"},
-           "e2e": {"value": value, "unit": "subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            runs.append(r)
+    tot_t = sum(r["wall_s"] for r in runs)
+    value = n_sample * len(runs) / tot_t
+    last = runs[-1]
+    cfg = shared_config(n_sample)
+    cfg.update({"subframes_per_step": n_sample, "turbo": "reference turbo_decode (3 SISO Viterbi passes; the reference has no iterative decoder)",
+                "fft": "single-precision radix-4 Stockham stand-in for FFTW3f (oracle/fftw3_shim)", "build": last["build"],
+                "parallelism": "%d host threads (std::thread pool, one LIBLTE_PHY_STRUCT each); only rank 0 runs" % threads})
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 2),
+           "unit": "subframes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * tot_t / len(runs), 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OFDM/CE/ZF) + int8 (reference turbo_decode)", "data": "synthetic",
+           "config": cfg,
+           "cpu_baseline": {"value": round(value, 2), "unit": "subframes/s", "cores": threads, "kind": last["kind"],
+                            "sample": f"{n_sample} subframes per step x {len(runs)} steps over {threads} threads, one LIBLTE_PHY_STRUCT per thread; {last['note']}",
+                            "value_1core": round(one["rate"], 2), "logical_cpus": logical, "physical_cores": physical_cores()},
+           "e2e": {"value": round(value, 2), "unit": "subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -214,7 +228,8 @@ def main():
     ap.add_argument("--n-sf", type=int, default=4000, help="subframes per step per GPU")
     ap.add_argument("--turbo-mode", type=int, default=1, help="1: 8-iteration max-log-MAP (headline), 0: reference-exact decoder")
     ap.add_argument("--iters", type=int, default=8)
-    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: subframes per step (default: about --ref-seconds of CPU wall time)")
+    ap.add_argument("--ref-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-pass", action="store_true", help="stop after the device-resident timed steps (for the ncu launch list of the step)")
     args = ap.parse_args()
@@ -414,29 +429,34 @@ def main():
     cpu = None
     os.sched_setaffinity(0, affinity_all)
     if rank == 0 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_sample = min(max(8 * threads, 64), n_sf - 1)
-        i_f = np.ascontiguousarray(iq[: (n_sample + 1) * SF_SAMPS + 8192, 0].astype(np.float32)); q_f = np.ascontiguousarray(iq[: (n_sample + 1) * SF_SAMPS + 8192, 1].astype(np.float32))
-        r, kind, okc, dt = cpu_reference_rate(i_f, q_f, start, subfr, n_sample, threads, tb_seg, seg=n_sf)
-        r1, _, ok1, dt1 = cpu_reference_rate(i_f, q_f, start, subfr, 16, 1, tb_seg, seg=n_sf)
-        stages_1core = cpu_stage_times(i_f, q_f, start, subfr, 8)
-        all_threads = {"value": round(r, 2), "cores": threads, "wall_s": round(dt, 2), "subframes": n_sample}
-        if r1 > r:
-            r, okc, dt, threads, n_sample = r1, ok1, dt1, 1, 16
-        cpu = {"value": round(r, 2), "unit": "subframes/s", "cores": threads, "kind": kind,
-               "sample": f"{n_sample} subframes of the same workload over {threads} threads ({dt:.2f} s wall), reference turbo_decode, FFT = oracle/fftw3_shim; {okc}",
-               "value_1core": round(r1, 2), "all_threads": all_threads, "stage_ms_per_subframe_1core": stages_1core}
+        logical = os.cpu_count() or 1
+        n_have = min(max(8 * logical, 256), n_sf - 1)
+        i_f = np.ascontiguousarray(iq[: (n_have + 1) * SF_SAMPS + 8192, 0].astype(np.float32)); q_f = np.ascontiguousarray(iq[: (n_have + 1) * SF_SAMPS + 8192, 1].astype(np.float32))
+        threads, _ = best_thread_count(i_f, q_f, start, subfr, tb_seg, n_sf)
+        probe = cpu_reference_rate(i_f, q_f, start, subfr, max(2 * threads, 16), threads, tb_seg, seg=n_sf)
+        n_sample = int(min(n_have, max(4 * threads, 32, probe["rate"] * 8.0)))       # about 8 s of wall time on all cores
+        r = cpu_reference_rate(i_f, q_f, start, subfr, n_sample, threads, tb_seg, seg=n_sf)
+        r1 = cpu_reference_rate(i_f, q_f, start, subfr, 32, 1, tb_seg, seg=n_sf)
+        stage = None
+        if r1["front_s"] is not None:
+            stage = {"liblte_phy_get_dl_subframe_and_ce (16 FFTs + channel estimate)": round(1e3 * r1["front_s"] / 32, 3),
+                     "liblte_phy_pdsch_channel_decode x %d allocations (demod + rate unmatch + turbo_decode + CRC)" % n_alloc: round(1e3 * r1["pdsch_s"] / 32, 3)}
+        cpu = {"value": round(r["rate"], 2), "unit": "subframes/s", "cores": threads, "kind": r["kind"],
+               "sample": f"{n_sample} subframes of the same workload over {threads} native threads ({r['wall_s']:.2f} s wall), reference turbo_decode, FFT = oracle/fftw3_shim, build {r['build']}; {r['note']}",
+               "value_1core": round(r1["rate"], 2), "logical_cpus": logical, "physical_cores": physical_cores(), "stage_ms_per_subframe_1core": stage}
 
     if rank == 0:
         total = world * n_sf * args.steps
-        out = {"metric": "DL subframes/sec (20MHz,64QAM,K=6144,8 turbo iters) @1/2/4/8 GPU vs CPU ref", "value": round(total / (ms * 1e-3), 1),
+        cfg = shared_config(n_sf)
+        cfg.update({"subframes_per_step_per_gpu": n_sf,
+                    "turbo": "max-log-MAP x%d" % args.iters if args.turbo_mode else "reference-exact (3 SISO passes)",
+                    "input_bytes_per_step_per_gpu": int(iq.nbytes), "l2_policy": "inputs larger than L2 (%.0f MB > 126 MB)" % (iq.nbytes / 1e6),
+                    "parallelism": f"{world} independent replicas, no data-path collective"})
+        out = {"metric": METRIC, "value": round(total / (ms * 1e-3), 1),
                "unit": "subframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OFDM/CE/ZF) + int8/int32 (turbo)",
                "data": "synthetic: %d distinct subframes per GPU from the library's own device-side transmit chain (bit-exact with the reference transmitter), int8 capture format, ~30 dB SNR" % n_sf,
-               "config": {"workload": WORKLOAD, "subframes_per_step_per_gpu": n_sf, "code_blocks_per_subframe": n_alloc, "K": K_CB,
-                          "turbo": "max-log-MAP x%d" % args.iters if args.turbo_mode else "reference-exact (3 SISO passes)", "iq_format": "int8 pairs",
-                          "input_bytes_per_step_per_gpu": int(iq.nbytes), "l2_policy": "inputs larger than L2 (%.0f MB > 126 MB)" % (iq.nbytes / 1e6),
-                          "parallelism": f"{world} independent replicas, no data-path collective"},
+               "config": cfg,
                "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "subframes/s", "h2d_bytes_per_step": int(iq.nbytes), "d2h_bytes_per_step": int(h_tb.numel() + h_ok.numel() * 4),
                        "ms_per_step": round(ms_e2e / args.steps, 4), "api": "lteb200_dl_receive_host (host pointers)", "host_placement": numa_note,
                        "timing": "median of 3 repeats of %d steps" % args.steps, "ms_per_step_all_repeats": [round(x / args.steps, 4) for x in e2e_runs], "results_ok": e2e_ok},

@@ -87,7 +87,8 @@ extern "C" int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_s
     const long long start = (long long)(uint32_t)(frame_start_idx + (uint32_t)subfr_num * (uint32_t)n_sf_samps);
     // only the window [start, start + subframe + 2 symbols + margin) travels to the device
     const long long lo = start > 0 ? start - 1 : 0;
-    long long hi = start + n_sf_samps + 3LL * ((128 << fs_idx) + (10 << fs_idx));   // symbols 14-15 of the window
+    // last sample the reference reads: symbol 1 of the next subframe ends at start + subframe + (N + cp0) + (N + cpe) - 1 (liblte_phy.cc:5946-5957, 8621)
+    long long hi = start + n_sf_samps + 2LL * (128 << fs_idx) + (10 << fs_idx) + (9 << fs_idx);
     if (hi > n_samps) hi = n_samps;
     if (lo >= hi) { lteb200_set_error(ctx, "subframe lies outside the sample buffer"); return LTEB200_ERR_ARGS; }
     const long long n = hi - lo;
@@ -285,7 +286,14 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     // stage 1: sample slices, back to back.  Chunk c's copy ends `halo` samples into chunk c+1; the next copy continues from there.
     long long copied = 0;
     for (int c = 0; c < n_chunks; c++) {
-        long long hi = c + 1 < n_chunks ? h_start_idx[bounds[c + 1]] + halo : n_samps;
+        // everything the chunk's LAST subframe reads (its 14 symbols + the two look-ahead symbols), and at least up to the halo of the
+        // next chunk's first subframe: with gapped, duplicate or overlapping start indices the former is the larger one
+        long long hi = n_samps;
+        if (c + 1 < n_chunks) {
+            hi = h_start_idx[bounds[c + 1]] + halo;
+            const long long last_end = h_start_idx[bounds[c + 1] - 1] + (1920LL << fs_idx) + halo;
+            if (last_end > hi) hi = last_end;
+        }
         if (hi > n_samps) hi = n_samps;
         if (hi > copied) {
             LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * copied, (const char *)h_iq + samp_bytes * copied, samp_bytes * (size_t)(hi - copied),

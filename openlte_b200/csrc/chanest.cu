@@ -208,6 +208,10 @@ int chan_est_launch(lteb200_ctx *ctx, const float *d_grid, const int *d_subfr_nu
         lteb200_set_error(ctx, "chan_est: bad N_ant/N_id_cell");
         return LTEB200_ERR_ARGS;
     }
+    if (N_rb_dl < 1 || N_rb_dl > 100) {      // rows of the shared-memory planes hold 1200 subcarriers
+        lteb200_set_error(ctx, "chan_est: N_rb_dl = %d outside 1..100", N_rb_dl);
+        return LTEB200_ERR_ARGS;
+    }
     float2 *crs = nullptr;
     int rc = get_crs_table(ctx, N_id_cell, &crs);
     if (rc) return rc;

@@ -46,6 +46,7 @@ struct lteb200_ctx {
     size_t       arena_bytes;
     std::map<int, QppTables> qpp;
     std::map<int, MlmTables> mlm;
+    std::map<int, uint16_t *> mlm2;   // pair kernel (turbo_mlm2.cu): 2 * position of pi(k) per position of k
     std::map<std::vector<int>, RateUnmatchMap> rum;
     cudaStream_t s_h2d, s_comp, s_d2h, s_front;   // pipeline streams of the host-pointer entry point (lazily created)
     float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)

@@ -60,6 +60,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_front); }
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) cudaFree(kv.second.piT);   // one blob: piT | csr_start | csr_pos
+    for (auto &kv : c->mlm2) cudaFree(kv.second);
     for (auto &kv : c->rum) cudaFree(kv.second.first_k);
     delete c;
 }

@@ -99,7 +99,8 @@ LIBLTE_ERROR_ENUM liblte_phy_get_dl_subframe_and_ce(LIBLTE_PHY_STRUCT *p, float 
 {
     if (!p || !i_samps || !q_samps || !(N_ant == 1 || N_ant == 2 || N_ant == 4) || !sf) return LIBLTE_ERROR_INVALID_INPUTS;
     const uint32 start = frame_start_idx + (uint32)subfr_num * p->N_samps_per_subfr;
-    const long long need = (long long)start + p->N_samps_per_subfr + 3LL * (p->N_samps_per_symb + p->N_samps_cp_l_0);
+    // the last sample the reference reads is the end of symbol 1 of the NEXT subframe (liblte_phy.cc:5946-5957, 8621): nothing beyond it is touched here
+    const long long need = (long long)start + p->N_samps_per_subfr + 2LL * p->N_samps_per_symb + p->N_samps_cp_l_0 + p->N_samps_cp_l_else;
     sf->num = subfr_num;
     int rc = lteb200_get_dl_subframe_and_ce(C_(p), i_samps, q_samps, need, p->b200_fs_idx, (int)p->N_rb_dl, frame_start_idx, subfr_num, N_id_cell, N_ant,
                                             &sf->rx_symb_re[0][0], &sf->rx_symb_im[0][0], &sf->rx_ce_re[0][0][0], &sf->rx_ce_im[0][0][0]);
@@ -141,7 +142,7 @@ LIBLTE_ERROR_ENUM liblte_phy_pdcch_channel_decode(LIBLTE_PHY_STRUCT *p, LIBLTE_P
                                                   LIBLTE_PHY_PHICH_STRUCT *phich, LIBLTE_PHY_PDCCH_STRUCT *pdcch)
 {
     if (!p || !sf || !pcfich || !phich || !pdcch) return LIBLTE_ERROR_INVALID_INPUTS;
-    static lteb200_dci dci[6];
+    lteb200_dci dci[6];            // per call: distinct phy structs may be used from distinct threads
     uint32 cfi = 0, n_symbs = 0, n_alloc = 0;
     const int rc = lteb200_pdcch_channel_decode(C_(p), &sf->rx_symb_re[0][0], &sf->rx_symb_im[0][0], &sf->rx_ce_re[0][0][0], &sf->rx_ce_im[0][0][0],
                                                 (int)p->N_rb_dl, sf->num, N_id_cell, N_ant, phich_res, (int)phich_dur, &cfi, &n_symbs, dci, &n_alloc);

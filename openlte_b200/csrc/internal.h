@@ -26,3 +26,9 @@ static inline int mlm_size_class(int K)
     const int nw = (K + 15) / 16;
     return nw <= 64 ? 64 : (nw <= 128 ? 128 : (nw <= 192 ? 192 : 384));
 }
+
+// Pair-lane formulation of the max-log-MAP kernel (turbo_mlm2.cu): block sizes that are multiples of 32 (every K >= 1024)
+struct FusedParams;
+bool mlm2_handles(int K);
+int mlm2_fused_capacity(int K);                  // soft bits the fused receive kernel can stage for this block size
+int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream);

@@ -258,7 +258,9 @@ int fs_legal(int fs_idx, int N_rb_dl)
     // liblte_phy_update_n_rb_dl, liblte_phy.cc:2601-2641
     if (fs_idx < 0 || fs_idx > 4) return 0;
     switch (fs_idx) {
-    case 4: return N_rb_dl >= 1 && N_rb_dl <= 110 && 12 * N_rb_dl < 2048;
+    // the reference accepts any N_rb_dl here, but its own subframe struct has rows of 1200 subcarriers (liblte_phy.h:226-239): 100 is the
+    // widest carrier that exists (and what the grid / estimate planes and the estimator's shared memory are sized for)
+    case 4: return N_rb_dl >= 1 && N_rb_dl <= 100;
     case 3: return N_rb_dl == 50 || N_rb_dl == 25 || N_rb_dl == 15 || N_rb_dl == 6;
     case 2: return N_rb_dl == 25 || N_rb_dl == 15 || N_rb_dl == 6;
     case 1: return N_rb_dl == 15 || N_rb_dl == 6;

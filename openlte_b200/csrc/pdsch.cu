@@ -287,7 +287,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant != 0) fusable = false;
         // the fused kernel stages an allocation's soft bits in the shared memory of its forward-metric store: 64 floats per window column
         const int NT = mlm_size_class(T[a].K);
-        if (T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;
+        if (T[a].M[2] * T[a].Qm > (mlm2_handles(T[a].K) ? mlm2_fused_capacity(T[a].K) : 64 * NT)) fusable = false;
     }
     if (fusable) {
         int *d_sn = nullptr;

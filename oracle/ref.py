@@ -269,6 +269,55 @@ class RefPhy:
         return err, cfi.value, allocs
 
 
+_native = None
+
+
+def native_lib():
+    """The -march=native build of the same reference sources (oracle/Makefile), loaded only where the host CPU has every flag of the
+    build host; otherwise the portable build.  Used by bench.py's CPU arm only."""
+    global _native
+    if _native is None:
+        so = os.path.join(_HERE, "_ref", "libref_oracle_native.so")
+        fl = os.path.join(_HERE, "_ref", "native_flags.txt")
+        ok = False
+        if os.path.exists(so) and os.path.exists(fl):
+            try:
+                need = set(open(fl).read().split())
+                have = set()
+                for ln in open("/proc/cpuinfo"):
+                    if ln.startswith("flags"):
+                        have = set(ln.split(":", 1)[1].split())
+                        break
+                ok = need <= have
+            except OSError:
+                ok = False
+        _native = (C.CDLL(so), "-O3 -march=native") if ok else (lib(), "-O3 -march=x86-64-v3")
+        _native[0].ref_chain_pool.restype = C.c_int
+    return _native
+
+
+def chain_pool(n_threads, i_samps, q_samps, start, subfr, allocs, cell, cfi, n_rb=100, fs=30.72, want_tb=None, seg=1):
+    """Native std::thread pool over subframes (ref_wrap.cc: ref_chain_pool): the reference's liblte_phy_get_dl_subframe_and_ce + PDSCH
+    receive of every allocation.  Returns dict(seconds, fails, front_s, pdsch_s, flags)."""
+    L, flags = native_lib()
+    n_sf = len(start)
+    desc = np.zeros((len(allocs), 114), np.int32)
+    for a, al in enumerate(allocs):
+        desc[a, 0] = al["mod"]; desc[a, 1] = al["tbs"]; desc[a, 2] = al["rnti"]; desc[a, 3] = len(al["prb"]); desc[a, 4:4 + len(al["prb"])] = al["prb"]
+    st = np.ascontiguousarray(start, np.int64); sn = np.ascontiguousarray(subfr, np.int32)
+    sec = C.c_double(0); stage = (C.c_double * 2)()
+    if want_tb is not None:
+        want_tb = np.ascontiguousarray(want_tb, np.uint8)
+        wt, stride = _p(want_tb), int(want_tb.shape[-1])
+    else:
+        wt, stride = None, 0
+    fails = L.ref_chain_pool(int(n_threads), FS[fs], int(n_rb), int(cell), int(cfi), _p(i_samps), _p(q_samps), n_sf, _p(st), _p(sn),
+                             len(allocs), _p(desc), wt, int(seg), stride, C.byref(sec), stage)
+    if fails < 0:
+        raise RuntimeError("liblte_phy_init failed inside ref_chain_pool")
+    return dict(seconds=sec.value, fails=int(fails), front_s=stage[0], pdsch_s=stage[1], flags=flags)
+
+
 def prs_c(c_init, n):
     out = np.zeros(n, np.uint32)
     lib().ref_generate_prs_c(C.c_uint(c_init), n, _p(out))

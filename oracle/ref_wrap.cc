@@ -19,6 +19,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
 #include "liblte_phy.h"
 
 extern "C" void *__wrap_malloc(size_t n) { return calloc(1, n ? n : 1); } /* -Wl,--wrap=malloc */
@@ -270,20 +274,33 @@ int ref_dlsch_channel_encode(void *h, const uint8 *tb_bits, int tbs, int tx_mode
  * driven through the reference's STAGE functions with caller-sized buffers, because its fixed scratch
  * (5000 REs / 10000 bits, liblte_phy.h:349-363) overruns for G > 10000 (H6).  Single antenna port.
  * The RE walk below is the loop at liblte_phy.cc:3745-3802 for N_ant == 1 in a non-0/5 subframe or any
- * subframe when the PRBs avoid the centre band; it is the only logic restated here. */
-int ref_pdsch_decode_big(void *h, void *subframe, int N_pdcch_symbs, int N_id_cell, int mod_type, int N_prb,
-                         const int *prb, int tbs, int rv_idx, int rnti, int tx_mode, uint8 *out_bits, int *N_out_bits,
-                         signed char *soft_out /* may be NULL */)
+ * subframe when the PRBs avoid the centre band; it is the only logic restated here.
+ * The scratch is caller-owned (BigScratch) so that a timing loop performs no allocation per transport block. */
+struct BigScratch {
+    int     maxre;
+    float  *f;      /* 8 planes of maxre floats */
+    int8   *soft;
+    uint32 *c;
+    float  *desc;
+};
+static void big_scratch_init(BigScratch *s, int N_prb)
 {
-    LIBLTE_PHY_STRUCT *p = (LIBLTE_PHY_STRUCT *)h;
-    LIBLTE_PHY_SUBFRAME_STRUCT *sf = (LIBLTE_PHY_SUBFRAME_STRUCT *)subframe;
-    const int maxre = 12 * 14 * N_prb;
-    float *y_re = (float *)malloc(sizeof(float) * maxre * 8);
-    float *y_im = y_re + maxre, *c_re = y_im + maxre, *c_im = c_re + maxre;
+    s->maxre = 12 * 14 * N_prb;
+    s->f     = (float *)malloc(sizeof(float) * (size_t)s->maxre * 8);
+    s->soft  = (int8 *)malloc((size_t)s->maxre * 6);
+    s->c     = (uint32 *)malloc(sizeof(uint32) * (size_t)s->maxre * 6);
+    s->desc  = (float *)malloc(sizeof(float) * (size_t)s->maxre * 6);
+}
+static void big_scratch_free(BigScratch *s) { free(s->f); free(s->soft); free(s->c); free(s->desc); }
+
+static int pdsch_decode_big_core(LIBLTE_PHY_STRUCT *p, LIBLTE_PHY_SUBFRAME_STRUCT *sf, BigScratch *s, int N_pdcch_symbs, int N_id_cell,
+                                 int mod_type, int N_prb, const int *prb, int tbs, int rv_idx, int rnti, int tx_mode, uint8 *out_bits,
+                                 int *N_out_bits, signed char *soft_out)
+{
+    const int maxre = s->maxre;
+    float *y_re = s->f, *y_im = y_re + maxre, *c_re = y_im + maxre, *c_im = c_re + maxre;
     float *x_re = c_im + maxre, *x_im = x_re + maxre, *d_re = x_im + maxre, *d_im = d_re + maxre;
-    int8   *soft = (int8 *)malloc((size_t)maxre * 6);
-    uint32 *c    = (uint32 *)malloc(sizeof(uint32) * (size_t)maxre * 6);
-    float  *desc = (float *)malloc(sizeof(float) * (size_t)maxre * 6);
+    int8 *soft = s->soft; uint32 *c = s->c; float *desc = s->desc;
     uint32 idx = 0, M_layer = 0, M_symb = 0, N_bits = 0, n_out = 0;
     uint32 first_sc, last_sc;
     if (p->N_rb_dl == 6) { first_sc = 0; last_sc = 71; }
@@ -318,8 +335,91 @@ int ref_pdsch_decode_big(void *h, void *subframe, int N_pdcch_symbs, int N_id_ce
     memset(p->td_in_calc_3, 0, sizeof(p->td_in_calc_3));
     int err = (int)dlsch_channel_decode(p, desc, N_bits, tbs, tx_mode, rv_idx, 8, 250368, out_bits, &n_out);
     *N_out_bits = (int)n_out;
-    free(y_re); free(soft); free(c); free(desc);
     return err == LIBLTE_SUCCESS ? 0 : (int)LIBLTE_ERROR_DECODE_FAIL;
+}
+int ref_pdsch_decode_big(void *h, void *subframe, int N_pdcch_symbs, int N_id_cell, int mod_type, int N_prb,
+                         const int *prb, int tbs, int rv_idx, int rnti, int tx_mode, uint8 *out_bits, int *N_out_bits,
+                         signed char *soft_out /* may be NULL */)
+{
+    BigScratch s;
+    big_scratch_init(&s, N_prb);
+    int err = pdsch_decode_big_core((LIBLTE_PHY_STRUCT *)h, (LIBLTE_PHY_SUBFRAME_STRUCT *)subframe, &s, N_pdcch_symbs, N_id_cell, mod_type,
+                                    N_prb, prb, tbs, rv_idx, rnti, tx_mode, out_bits, N_out_bits, soft_out);
+    big_scratch_free(&s);
+    return err;
+}
+
+/* Native thread pool over subframes for the CPU arm of bench.py: n_threads std::threads, ONE LIBLTE_PHY_STRUCT,
+ * subframe struct and scratch per thread, all created SERIALLY before the clock starts (FFT planning is not thread safe); subframes are
+ * handed out through an atomic counter.  Per subframe: liblte_phy_get_dl_subframe_and_ce, then the PDSCH receive of every allocation.
+ *   alloc_desc: n_alloc records of {mod_type, tbs, rnti, N_prb, prb[0..110)} (114 ints each)
+ *   want_tb   : expected transport blocks [seg][n_alloc][tb_stride] (NULL: only the CRC verdict counts); subframe b is compared with
+ *               want_tb[b % seg]
+ * Returns the number of transport blocks that failed (CRC or bits); *seconds = wall time of the parallel region,
+ * stage_s[0..1] = summed per-thread seconds in the front end and in the PDSCH receive. */
+int ref_chain_pool(int n_threads, int fs_enum, int N_rb_dl, int N_id_cell, int cfi, const float *i_samps, const float *q_samps,
+                   int n_sf, const long long *start_idx, const int *subfr_num, int n_alloc, const int *alloc_desc,
+                   const uint8 *want_tb, int seg, int tb_stride, double *seconds, double *stage_s)
+{
+    struct Worker { LIBLTE_PHY_STRUCT *phy; LIBLTE_PHY_SUBFRAME_STRUCT *sf; BigScratch scr; uint8 *bits; int fails; double t_front, t_pdsch; };
+    if (n_threads < 1) n_threads = 1;
+    std::vector<Worker> w(n_threads);
+    int max_prb = 1;
+    for (int a = 0; a < n_alloc; a++) if (alloc_desc[114 * a + 3] > max_prb) max_prb = alloc_desc[114 * a + 3];
+    for (int t = 0; t < n_threads; t++) {
+        w[t].phy = NULL;
+        if (LIBLTE_SUCCESS != liblte_phy_init(&w[t].phy, (LIBLTE_PHY_FS_ENUM)fs_enum, (uint16)N_id_cell, 1, (uint32)N_rb_dl,
+                                              LIBLTE_PHY_N_SC_RB_DL_NORMAL_CP, 1.0f))
+            return -1;
+        w[t].sf = (LIBLTE_PHY_SUBFRAME_STRUCT *)calloc(1, sizeof(LIBLTE_PHY_SUBFRAME_STRUCT));
+        big_scratch_init(&w[t].scr, max_prb);
+        w[t].bits = (uint8 *)malloc(LIBLTE_PHY_MAX_CODE_BLOCK_SIZE + 64);
+        w[t].fails = 0; w[t].t_front = w[t].t_pdsch = 0.0;
+    }
+    const uint32 n_sf_samps = w[0].phy->N_samps_per_subfr;
+    std::atomic<int> next(0), ready(0);
+    std::atomic<bool> go(false);
+    auto body = [&](int t) {
+        ready.fetch_add(1);
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        Worker &me = w[t];
+        for (;;) {
+            const int b = next.fetch_add(1);
+            if (b >= n_sf) break;
+            const int sn = subfr_num[b];
+            /* liblte_phy_get_dl_subframe_and_ce addresses a subframe as frame_start_idx + subfr_num*N (uint32 arithmetic) */
+            const uint32 fstart = (uint32)((unsigned long long)start_idx[b] - (unsigned long long)sn * n_sf_samps);
+            auto t0 = std::chrono::steady_clock::now();
+            liblte_phy_get_dl_subframe_and_ce(me.phy, (float *)i_samps, (float *)q_samps, fstart, (uint8)sn, N_id_cell, 1, me.sf);
+            auto t1 = std::chrono::steady_clock::now();
+            for (int a = 0; a < n_alloc; a++) {
+                const int *d = alloc_desc + 114 * a;
+                int n_out = 0;
+                int err = pdsch_decode_big_core(me.phy, me.sf, &me.scr, cfi, N_id_cell, d[0], d[3], d + 4, d[1], 0, d[2], 1, me.bits, &n_out, NULL);
+                if (err != 0) me.fails++;
+                else if (want_tb && memcmp(me.bits, want_tb + ((size_t)(b % seg) * n_alloc + a) * tb_stride, (size_t)d[1]) != 0) me.fails++;
+            }
+            auto t2 = std::chrono::steady_clock::now();
+            me.t_front += std::chrono::duration<double>(t1 - t0).count();
+            me.t_pdsch += std::chrono::duration<double>(t2 - t1).count();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(body, t);
+    while (ready.load() < n_threads) std::this_thread::yield();
+    auto T0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto &x : th) x.join();
+    auto T1 = std::chrono::steady_clock::now();
+    *seconds = std::chrono::duration<double>(T1 - T0).count();
+    int fails = 0;
+    double tf = 0, tp = 0;
+    for (int t = 0; t < n_threads; t++) {
+        fails += w[t].fails; tf += w[t].t_front; tp += w[t].t_pdsch;
+        liblte_phy_cleanup(w[t].phy); free(w[t].sf); big_scratch_free(&w[t].scr); free(w[t].bits);
+    }
+    if (stage_s) { stage_s[0] = tf; stage_s[1] = tp; }
+    return fails;
 }
 
 /* ----------------------------------------------------------------- TX side */
