@@ -106,6 +106,18 @@ __device__ __forceinline__ uint32_t bwd_step(uint32_t (&b)[8], const uint32_t (&
     return vsub(L0, L1);
 }
 
+// Equalised symbol -> demapped, descrambled soft bits of one resource element (the reference's int8 soft bits times +-1,
+// liblte_phy.cc:9502-9660, :3831-3836).  Not inlined: the demapper (atan2f for QPSK) would otherwise be replicated at every call site and the
+// input phase, executed once per block, would be mostly instruction-cache misses.
+__device__ __noinline__ void emit_soft(float xr, float xi, int mod, int Qm, const uint8_t *__restrict__ cs_r, int8_t *soft_r)
+{
+    int bb[6];
+    demap_bits(xr, xi, mod, bb);
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
+}
+
 // extrinsic of one lane: clamp(((L - Lsa) * 3) >> 2)
 __device__ __forceinline__ int ext_of(int d) { return clampi((d * 3) >> 2, -LE_LIM, LE_LIM); }
 
@@ -263,11 +275,8 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
         const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
         const int *ix = A.re_idx + cls * A.idx_stride;
         const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
-        auto emit = [&](int r, float xr, float xi) {
-            int bb[6];
-            demap_bits(xr, xi, A.mod, bb);
-            for (int q = 0; q < A.Qm; q++) soft[r * A.Qm + q] = (int8_t)(cs[r * A.Qm + q] ? -bb[q] : bb[q]);
-        };
+        const int Qm = A.Qm, mod = A.mod;
+        auto emit = [&](int r, float xr, float xi) { emit_soft(xr, xi, mod, Qm, cs + r * Qm, soft + r * Qm); };
         if (fp.N_ant != 1) {
             // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
             const size_t ps = (size_t)14 * fp.nsc;
@@ -310,10 +319,18 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
         // float with the sentinel 10000 for "nothing received"; the soft bits are small integers, so integer sums are exact and the
         // sentinel comparisons are restated on the integers (a running sum that hits 10000 exactly is replaced, as there).
         constexpr int NUL = 10000;
+        const int period = A.period;
+        const bool two_visits = E <= 2 * period;          // every output is visited at most twice: v = x0 + x1, no sentinel can arise
         auto unmatch = [&](int fk) -> int {
+            if (two_visits) {
+                const int k1 = fk + period;
+                const int x0 = (fk >= 0 && fk < E) ? soft[fk] : 0, x1 = (fk >= 0 && k1 < E) ? soft[k1] : 0;
+                return x0 + x1;
+            }
             int w = NUL;
             if (fk >= 0)
-                for (int k = fk; k < E; k += A.period) {
+#pragma unroll 1
+                for (int k = fk; k < E; k += period) {
                     const int x = soft[k];
                     w = (w == NUL) ? x : w + x;
                 }
@@ -380,6 +397,20 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
     }
     __syncthreads();
     const float maxv = s_red[0];
+    // Fused path: the un-matched values are integers with |v| <= maxv, so the reference's quantisation q(v) = trunc(v * 127 / maxv)
+    // (liblte_phy.cc:10645-10664, IEEE multiply and divide) is tabulated once per block for 0..maxv (q is odd) instead of dividing
+    // 18,444 times; the table sits in the (not yet staged) interleaver-table area.  Larger ranges divide directly.
+    int8_t *lut = reinterpret_cast<int8_t *>(sm.piT2);
+    const int maxi = FUSED ? (int)maxv : 0;
+    const bool use_lut = FUSED && maxi < 2 * NP;
+    if (FUSED) {
+        if (use_lut) for (int p = t; p <= maxi; p += nt) lut[p] = (int8_t)qf((float)p, maxv);
+        __syncthreads();
+    }
+    auto q_int = [&](int v) -> int {
+        if (use_lut) { const int q = lut[abs(v)]; return v < 0 ? -q : q; }
+        return qf((float)v, maxv);
+    };
     // ---- quantise into the window-transposed arrays: thread t writes the (2t, 2t+1) word of every row
     if (active) {
         uint16_t *Ls16 = reinterpret_cast<uint16_t *>(sm.Ls) + t, *Lp116 = reinterpret_cast<uint16_t *>(sm.Lp1) + t, *Lp216 = reinterpret_cast<uint16_t *>(sm.Lp2) + t;
@@ -394,9 +425,9 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
             // every thread's own Y words are in registers now; S1 / Ls / Lp alias the (dead) soft bits, not Y
 #pragma unroll
             for (int i = 0; i < WIN; i++) {
-                const int sA = qf((float)lo16(y[0][i]), maxv), sB = qf((float)hi16(y[0][i]), maxv);
-                const int pA = qf((float)lo16(y[1][i]), maxv), pB = qf((float)hi16(y[1][i]), maxv);
-                const int rA = qf((float)lo16(y[2][i]), maxv), rB = qf((float)hi16(y[2][i]), maxv);
+                const int sA = q_int(lo16(y[0][i])), sB = q_int(hi16(y[0][i]));
+                const int pA = q_int(lo16(y[1][i])), pB = q_int(hi16(y[1][i]));
+                const int rA = q_int(lo16(y[2][i])), rB = q_int(hi16(y[2][i]));
                 Ls16[i * NT2] = (uint16_t)((sA & 0xff) | ((sB & 0xff) << 8));
                 Lp116[i * NT2] = (uint16_t)((pA & 0xff) | ((pB & 0xff) << 8));
                 Lp216[i * NT2] = (uint16_t)((rA & 0xff) | ((rB & 0xff) << 8));
@@ -433,7 +464,7 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
         }
     }
     if (t < 12) s_tail[t] = qf(tail_v, maxv);                // s_tail[3*r + x] = q(d_x[K+r])
-    if (FUSED) __syncthreads();                             // Y[] (over recA | recB | acc) is dead from here on
+    if (FUSED) __syncthreads();                             // Y[] (over recA | recB | acc) and the quantisation table are dead from here on
     // ---- interleaver table, accumulators, boundary records
     for (int p = t; p < NP / 2; p += nt) reinterpret_cast<uint32_t *>(sm.piT2)[p] = reinterpret_cast<const uint32_t *>(piT2g)[p];
     for (int p = t; p < NP; p += nt) sm.acc[p] = 0;
@@ -534,16 +565,15 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
         uint32_t rem = 0;
         if (active) {
             const int idx0 = k0 - A.F;                                     // index of this thread's first bit inside [a | p]
-            const bool fast = idx0 >= 0 && idx0 + 2 * WIN <= A.tbs && (((size_t)(o + idx0)) & 15) == 0;
+            const bool fast = idx0 >= 0 && idx0 + 2 * WIN <= A.tbs && (((size_t)(o + idx0)) & 7) == 0;
             if (fast) {
-                uint32_t w[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t nb = (bits >> (4 * j)) & 0xfu;
-                    w[j] = (nb & 1u) | ((nb & 2u) << 7) | ((nb & 4u) << 14) | ((nb & 8u) << 21);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t b0 = (bits >> (8 * j)) & 0xfu, b1 = (bits >> (8 * j + 4)) & 0xfu;
+                    const uint32_t w0 = (b0 & 1u) | ((b0 & 2u) << 7) | ((b0 & 4u) << 14) | ((b0 & 8u) << 21);
+                    const uint32_t w1 = (b1 & 1u) | ((b1 & 2u) << 7) | ((b1 & 4u) << 14) | ((b1 & 8u) << 21);
+                    reinterpret_cast<uint2 *>(o + idx0)[j] = make_uint2(w0, w1);
                 }
-                reinterpret_cast<uint4 *>(o + idx0)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                reinterpret_cast<uint4 *>(o + idx0)[1] = make_uint4(w[4], w[5], w[6], w[7]);
             } else {
 #pragma unroll 4
                 for (int j = 0; j < 2 * WIN; j++) {
@@ -551,11 +581,11 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
                     if (idx >= 0 && idx < A.tbs) o[idx] = (uint8_t)((bits >> j) & 1u);
                 }
             }
-#pragma unroll 4
-            for (int j = 0; j < 2 * WIN; j++) {
-                const int idx = idx0 + j;
-                if (idx >= 0 && ((bits >> j) & 1u)) rem ^= fp.crc_tab[n - 1 - idx];
-            }
+            // 32 independent (predicated) table reads, all issued before the first is consumed
+            const uint32_t *ct = fp.crc_tab + (n - 1 - idx0);
+#pragma unroll
+            for (int j = 0; j < 2 * WIN; j++)
+                if (idx0 + j >= 0 && ((bits >> j) & 1u)) rem ^= ct[-j];
         }
         for (int off = 16; off > 0; off >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, off);
         if ((t & 31) == 0) s_tail[t >> 5] = (int)rem;                      // <= 6 warps
