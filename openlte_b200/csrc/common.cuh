@@ -31,6 +31,7 @@ struct QppTables {
 // Rate-(un)matching gather map for one (K, E, rv, N_cb) configuration.
 struct RateUnmatchMap {
     int32_t *first_k;    // [3*(K+4)] first e index feeding output d[3i+x], or -1
+    int32_t *first_kT;   // [3][16 NT] the same in window-transposed order (position (k mod 16) NT + k/16; -1 on padding) + [12] tail + [4] pad
     int      n_nonnull;  // period of the circular buffer in e indices
 };
 

@@ -30,5 +30,8 @@ static inline int mlm_size_class(int K)
 // Pair-lane formulation of the max-log-MAP kernel (turbo_mlm2.cu): block sizes that are multiples of 32 (every K >= 1024)
 struct FusedParams;
 bool mlm2_handles(int K);
-int mlm2_fused_capacity(int K);                  // soft bits the fused receive kernel can stage for this block size
-int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream);
+size_t mlm2_q8_stride(int K);                    // bytes of one quantised input image
+int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, const int8_t *q8, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused,
+                      cudaStream_t stream);
+// PDSCH symbol level + rate unmatching + quantisation into that image, one CTA per transport block (pdsch_llr.cu)
+int pdsch_llr_q8_launch(lteb200_ctx *ctx, const FusedParams &fp, int K, int E_max, int8_t *d_q8, cudaStream_t stream);

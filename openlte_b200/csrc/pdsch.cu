@@ -11,6 +11,7 @@
 // an index list per class; the kernel is then a fused gather -> ZF -> demap -> descramble, one thread per resource
 // element, reading grid and channel estimate once (8 B + 8 B) and writing Q_m floats: HBM-bound.
 #include "internal.h"
+#include <algorithm>
 #include "pdsch_dev.cuh"
 #include <math.h>
 
@@ -287,7 +288,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant != 0) fusable = false;
         // the fused kernel stages an allocation's soft bits in the shared memory of its forward-metric store: 64 floats per window column
         const int NT = mlm_size_class(T[a].K);
-        if (T[a].M[2] * T[a].Qm > (mlm2_handles(T[a].K) ? mlm2_fused_capacity(T[a].K) : 64 * NT)) fusable = false;
+        if (!mlm2_handles(T[a].K) && T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;    // (the pair kernel's symbol-level kernel stages any single-block allocation)
     }
     if (fusable) {
         int *d_sn = nullptr;
@@ -309,12 +310,23 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
                 FusedAlloc &A = fp.al[e - a];
                 A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.first_k = m.first_k; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
                 for (int c = 0; c < 3; c++) A.M[c] = T[e].M[c];
+                A.first_kT = m.first_kT;
                 A.Qm = T[e].Qm; A.mod = allocs[e].mod_type; A.period = m.n_nonnull; A.F = T[e].F; A.tbs = allocs[e].tbs; A.a_idx = e;
                 e++;
             }
             if (rc) break;
             fp.n_al = e - a;
-            rc = turbo_mlm_fused_batch(ctx, T[a].K, n_iter, fp, stream);
+            if (mlm2_handles(T[a].K)) {
+                // symbol level -> quantised LLR images (18 KB per K = 6144 block), then the pair-lane decoder with CRC + transport-block output
+                int E_max = 0;
+                for (int q = a; q < e; q++) E_max = std::max(E_max, T[q].M[2] * T[q].Qm);
+                int8_t *d_q8 = nullptr;
+                LTE_CUDA_OK(ctx, cudaMallocAsync(&d_q8, mlm2_q8_stride(T[a].K) * (size_t)fp.n_al * n_sf, stream));
+                rc = pdsch_llr_q8_launch(ctx, fp, T[a].K, E_max, d_q8, stream);
+                if (rc == LTEB200_OK) rc = turbo_mlm2_launch(ctx, nullptr, d_q8, T[a].K, fp.n_al * n_sf, n_iter, nullptr, &fp, stream);
+                cudaFreeAsync(d_q8, stream);
+            } else
+                rc = turbo_mlm_fused_batch(ctx, T[a].K, n_iter, fp, stream);
             a = e;
         }
         cudaFreeAsync(d_sn, stream);

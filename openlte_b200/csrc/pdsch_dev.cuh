@@ -90,6 +90,7 @@ struct FusedAlloc {
     const int *re_idx;        // [3][idx_stride]  PDSCH resource elements per subframe class (0, 5, other)
     const uint8_t *cseq;      // [10][c_stride]   scrambling bits per subframe number
     const int32_t *first_k;   // [3(K+4)]         rate-unmatch gather map
+    const int32_t *first_kT;  // the same in the decoder's window-transposed output order + 12 tail entries (pair kernel only)
     int idx_stride, c_stride;
     int M[3];
     int Qm, mod, period, F, tbs, a_idx;

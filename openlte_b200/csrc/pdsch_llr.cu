@@ -1,0 +1,163 @@
+// PDSCH symbol level for the max-log-MAP decoder: resource-element extraction, equalisation, demapping, descrambling, rate
+// unmatching and quantisation of ONE transport block per CTA, written as the int8 image the pair-lane decoder (turbo_mlm2.cu, MODE_Q8)
+// stages with a single bulk copy.  Reference functions restated: the RE walk of liblte_phy_pdsch_channel_decode
+// (liblte_phy.cc:3745-3802, index lists built on the host), pre_decoder_and_matched_filter_dl (:7645-7796), layer_demapper_dl (:7473),
+// modulation_demapper (:9502-9660), descrambling (:3831-3836), liblte_phy_rate_unmatch_turbo (:11246-11490) and the quantisation at the head
+// of turbo_decode (:10636-10664).
+//
+// Why its own kernel: this phase is a latency-bound gather (16 bytes per resource element from the grid and the estimate, then short
+// shared-memory walks) that wants many resident warps, while the decoder is ALU-bound with 168 registers per thread and two CTAs per SM.
+// Fused into the decoder (round 1, and the first version of the pair kernel) it left the ALU pipe idle half of the time
+// (profiles/r2_fused_vs_split.json); on its own it runs at 8+ CTAs per SM, and the decoder's input shrinks to 18 KB per block.
+//
+// The soft bits of a block stay in shared memory as int8 (the reference's demapper emits int8, descrambling multiplies by +-1), the sums of
+// repeated bits are exact in integers, and q(v) = trunc(v * 127 / max) -- IEEE multiply and divide as in the reference -- is tabulated once per
+// block for 0..max instead of being divided out 18,444 times.
+#include "internal.h"
+#include "pdsch_dev.cuh"
+
+namespace {
+
+__device__ __forceinline__ int qf(float v, float maxv) { return __float2int_rz(__fdiv_rn(__fmul_rn(v, 127.0f), maxv)); }  // NaN -> 0
+
+// Equalised symbol -> demapped, descrambled soft bits of one resource element.  Not inlined: the demapper (atan2f for QPSK) would otherwise be
+// replicated at every call site.
+__device__ __noinline__ void emit_soft(float xr, float xi, int mod, int Qm, const uint8_t *__restrict__ cs_r, int8_t *soft_r)
+{
+    int bb[6];
+    demap_bits(xr, xi, mod, bb);
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
+}
+
+constexpr int LUT_MAX = 2048;     // |v| range that is tabulated (127 x 16 repeats); beyond it the division is done per value
+
+// first_kT: gather map in OUTPUT order: [x][pos] for the three streams (pos = (k mod 16) * NT + k / 16, -1 on the padding) followed by the 12
+// tail entries d[3K + j].  q8 image per block: Ls[NP] | Lp1[NP] | Lp2[NP] | tail[16].
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_t *__restrict__ q8)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_red[32];
+    __shared__ int8_t lut[LUT_MAX];
+    const int cb = blockIdx.x, t = threadIdx.x;
+    const int a_loc = cb / fp.n_sf, sf = cb - a_loc * fp.n_sf;
+    const FusedAlloc &A = fp.al[a_loc];
+    const int sn = fp.subfr_num[sf];
+    const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
+    const int M = A.M[cls], Qm = A.Qm, mod = A.mod, E = M * Qm;
+    int8_t *soft = reinterpret_cast<int8_t *>(smem_raw);
+    const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
+    const int *ix = A.re_idx + cls * A.idx_stride;
+    const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
+    if (fp.N_ant != 1) {
+        // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
+        const size_t ps = (size_t)14 * fp.nsc;
+        for (int r = t * fp.N_ant; r < M; r += THREADS * fp.N_ant) {
+            if (fp.N_ant == 2) {
+                float2 x0, x1;
+                sfbc2(gr[ix[r]], gr[ix[r + 1]], ch[ix[r]], ch[ps + ix[r]], x0, x1);
+                emit_soft(x0.x, x0.y, mod, Qm, cs + r * Qm, soft + r * Qm);
+                emit_soft(x1.x, x1.y, mod, Qm, cs + (r + 1) * Qm, soft + (r + 1) * Qm);
+            } else {
+                const float2 y[4] = {gr[ix[r]], gr[ix[r + 1]], gr[ix[r + 2]], gr[ix[r + 3]]};
+                float2 x[4];
+                sfbc4(y, ch[ix[r]], ch[ps + ix[r + 2]], ch[2 * ps + ix[r]], ch[3 * ps + ix[r + 2]], x);
+                for (int q = 0; q < 4; q++) emit_soft(x[q].x, x[q].y, mod, Qm, cs + (r + q) * Qm, soft + (r + q) * Qm);
+            }
+        }
+    } else {
+        // indices, grid and estimate values of RE_IT elements are fetched before the arithmetic starts: the gather latency is paid once per round
+        constexpr int RE_IT = 4;
+        for (int r0 = t; r0 < M; r0 += RE_IT * THREADS) {
+            int idx[RE_IT];
+            float2 yv[RE_IT], hv[RE_IT];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) idx[u] = (r0 + u * THREADS < M) ? ix[r0 + u * THREADS] : ix[r0];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) { yv[u] = gr[idx[u]]; hv[u] = ch[idx[u]]; }
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) {
+                const int r = r0 + u * THREADS;
+                if (r < M) {
+                    float xr, xi;
+                    zf_1port(yv[u], hv[u], xr, xi);
+                    emit_soft(xr, xi, mod, Qm, cs + r * Qm, soft + r * Qm);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // rate unmatching (liblte_phy.cc:11403-11415): the first visit assigns, repeats are added in visiting order.  The reference works in float
+    // with the sentinel 10000 for "nothing received"; the soft bits are small integers, so integer sums are exact and the sentinel
+    // comparisons are restated on the integers (a running sum that hits 10000 exactly is replaced, as there).
+    constexpr int NUL = 10000;
+    const int period = A.period;
+    const bool two_visits = E <= 2 * period;          // every output is visited at most twice: v = x0 + x1, no sentinel can arise
+    auto unmatch = [&](int fk) -> int {
+        if (two_visits) {
+            const int k1 = fk + period;
+            const int x0 = (fk >= 0 && fk < E) ? soft[fk] : 0, x1 = (fk >= 0 && k1 < E) ? soft[k1] : 0;
+            return x0 + x1;
+        }
+        int w = NUL;
+        if (fk >= 0)
+#pragma unroll 1
+            for (int k = fk; k < E; k += period) {
+                const int x = soft[k];
+                w = (w == NUL) ? x : w + x;
+            }
+        return w == NUL ? 0 : w;                       // turbo_decode zeroes the sentinels (liblte_phy.cc:10636-10642)
+    };
+    // ---- pass 1: max |v| over the 3 K + 12 outputs (padding entries are -1 -> 0)
+    const int NP = 16 * NT, n_map = 3 * NP + 12;
+    const int *fkT = A.first_kT;
+    int mi = 0;
+    for (int j = t; j < n_map; j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
+    for (int o = 16; o > 0; o >>= 1) mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    if ((t & 31) == 0) s_red[t >> 5] = mi;
+    __syncthreads();
+    if (t < 32) {
+        int v = t < THREADS / 32 ? s_red[t] : 0;
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (t == 0) s_red[0] = v;
+    }
+    __syncthreads();
+    const int maxi = s_red[0];
+    const float maxv = (float)maxi;
+    const bool use_lut = maxi < LUT_MAX;
+    if (use_lut) for (int p = t; p <= maxi; p += THREADS) lut[p] = (int8_t)qf((float)p, maxv);
+    __syncthreads();
+    auto q_int = [&](int v) -> uint32_t {
+        int q;
+        if (use_lut) { q = lut[abs(v)]; q = v < 0 ? -q : q; } else q = qf((float)v, maxv);
+        return (uint32_t)q & 0xffu;
+    };
+    // ---- pass 2: quantised image, four consecutive output bytes per thread and round
+    int8_t *img = q8 + (size_t)cb * (3 * NP + 16);
+    const int4 *fk4 = reinterpret_cast<const int4 *>(fkT);
+    for (int j = t; j < 3 * NP / 4; j += THREADS) {
+        const int4 f = fk4[j];
+        const uint32_t w = q_int(unmatch(f.x)) | (q_int(unmatch(f.y)) << 8) | (q_int(unmatch(f.z)) << 16) | (q_int(unmatch(f.w)) << 24);
+        reinterpret_cast<uint32_t *>(img)[j] = w;
+    }
+    if (t < 16) img[3 * NP + t] = t < 12 ? (int8_t)q_int(unmatch(fkT[3 * NP + t])) : (int8_t)0;
+}
+
+}  // namespace
+
+// One CTA per transport block of the group described by fp (fp.n_al allocations of the same K, fp.n_sf subframes); q8 receives n_al * n_sf images.
+int pdsch_llr_q8_launch(lteb200_ctx *ctx, const FusedParams &fp, int K, int E_max, int8_t *d_q8, cudaStream_t stream)
+{
+    constexpr int THREADS = 256;
+    const int NT = mlm_size_class(K);
+    const size_t smem = ((size_t)E_max + 15) & ~(size_t)15;
+    if (smem > 200 * 1024) { lteb200_set_error(ctx, "PDSCH: %d soft bits per transport block exceed the shared-memory staging", E_max); return LTEB200_ERR_UNSUPPORTED; }
+    LTE_CUDA_OK(ctx, cudaFuncSetAttribute(pdsch_llr_q8_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pdsch_llr_q8_kernel<THREADS><<<fp.n_al * fp.n_sf, THREADS, smem, stream>>>(fp, K, NT, d_q8);
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    return LTEB200_OK;
+}

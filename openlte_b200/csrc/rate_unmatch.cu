@@ -8,7 +8,7 @@
 // onto it again.  The kernel is then one coalesced gather per output; repeats are soft-combined by addition in
 // the reference's visiting order (liblte_phy.cc:11407-11412), unfilled positions carry the 10000 sentinel.
 // HBM-bound: reads E floats, writes 3(K+4) floats per code block.
-#include "common.cuh"
+#include "internal.h"
 
 namespace {
 
@@ -111,6 +111,16 @@ int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int
     m.n_nonnull = rank;
     LTE_CUDA_OK(ctx, cudaMalloc(&m.first_k, sizeof(int32_t) * 3 * D));
     LTE_CUDA_OK(ctx, cudaMemcpy(m.first_k, first.data(), sizeof(int32_t) * 3 * D, cudaMemcpyHostToDevice));
+    {
+        // output order of the pair-lane decoder's input image (pdsch_llr.cu): three planes of 16 NT positions, then the 12 tail values
+        const int K = D - 4, NT = mlm_size_class(K), NP = 16 * NT;
+        std::vector<int32_t> T((size_t)3 * NP + 16, -1);
+        for (int k = 0; k < K; k++)
+            for (int x = 0; x < 3; x++) T[(size_t)x * NP + (k % 16) * NT + k / 16] = first[3 * k + x];
+        for (int j = 0; j < 12; j++) T[(size_t)3 * NP + j] = first[3 * K + j];
+        LTE_CUDA_OK(ctx, cudaMalloc(&m.first_kT, sizeof(int32_t) * T.size()));
+        LTE_CUDA_OK(ctx, cudaMemcpy(m.first_kT, T.data(), sizeof(int32_t) * T.size(), cudaMemcpyHostToDevice));
+    }
     ctx->rum[key] = m;
     *out = m;
     return LTEB200_OK;

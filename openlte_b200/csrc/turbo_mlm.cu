@@ -493,7 +493,7 @@ int turbo_mlm_fused_batch(lteb200_ctx *ctx, int K, int n_iter, const FusedParams
 static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream)
 {
     if (K < 40 || (K & 7) || K > 6144) { lteb200_set_error(ctx, "turbo: illegal K=%d", K); return LTEB200_ERR_ARGS; }
-    if (mlm2_handles(K)) return turbo_mlm2_launch(ctx, d_llr, K, n_cb, n_iter, d_bits, fused, stream);   // two windows per thread, register-resident metrics
+    if (mlm2_handles(K) && !fused) return turbo_mlm2_launch(ctx, d_llr, nullptr, K, n_cb, n_iter, d_bits, nullptr, stream);   // two windows per thread, register-resident metrics
     if (n_iter < 1) n_iter = 1;
     QppTables qt;
     int rc = lteb200_get_qpp(ctx, K, &qt);  // validates K

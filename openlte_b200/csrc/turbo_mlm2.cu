@@ -106,18 +106,6 @@ __device__ __forceinline__ uint32_t bwd_step(uint32_t (&b)[8], const uint32_t (&
     return vsub(L0, L1);
 }
 
-// Equalised symbol -> demapped, descrambled soft bits of one resource element (the reference's int8 soft bits times +-1,
-// liblte_phy.cc:9502-9660, :3831-3836).  Not inlined: the demapper (atan2f for QPSK) would otherwise be replicated at every call site and the
-// input phase, executed once per block, would be mostly instruction-cache misses.
-__device__ __noinline__ void emit_soft(float xr, float xi, int mod, int Qm, const uint8_t *__restrict__ cs_r, int8_t *soft_r)
-{
-    int bb[6];
-    demap_bits(xr, xi, mod, bb);
-#pragma unroll
-    for (int q = 0; q < 6; q++)
-        if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
-}
-
 // extrinsic of one lane: clamp(((L - Lsa) * 3) >> 2)
 __device__ __forceinline__ int ext_of(int d) { return clampi((d * 3) >> 2, -LE_LIM, LE_LIM); }
 
@@ -134,7 +122,8 @@ struct Smem {
     int acc[NP];            // sum of the second decoder's extrinsics per natural position (a-priori of the first decoder, unclamped)
     int16_t S1[NP];         // Lsys + Le1 (natural order): a-priori + systematic of the second decoder, read through pi
     uint16_t piT2[NP];      // 2 * position of pi(k), stored at the position of k (byte offset into S1)
-    int8_t Ls[NP], Lp1[NP], Lp2[NP];
+    int8_t Ls[NP], Lp1[NP], Lp2[NP];   // quantised channel LLRs; with tail8 one contiguous image (the Q8 input format)
+    int8_t tail8[16];                   // q(d_x[K + r]) at [3 r + x], 12 used
 };
 
 template <int NT, bool SECOND>
@@ -239,15 +228,42 @@ __device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool a
     __syncthreads();
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared with completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+constexpr int MODE_F32 = 0;   // input: rate-unmatched float LLRs llr[n_cb][3(K+4)] (quantised here);  output: decoded bits out[n_cb][K]
+constexpr int MODE_Q8 = 1;    // input: quantised, window-transposed LLR image q8[n_cb][3 NP + 16] written by pdsch_llr_q8_kernel (pdsch_llr.cu);
+                              // output: transport block bits + CRC24A verdict (block index = local_alloc * n_sf + subframe)
+
 // piT2 [16*NT] : 2 * pos(pi(k)) stored at pos(k)                                                     (global, per K)
-// FUSED == false: input = rate-unmatched LLRs llr[n_cb][3(K+4)], output = decoded bits out[n_cb][K].
-// FUSED == true : the whole PDSCH receive of one transport block: RE extraction, ZF / transmit-diversity combining, demapping and
-//                 descrambling into shared memory (int8: the reference's soft bits are int8 times +-1, liblte_phy.cc:9502, :3831), rate
-//                 unmatching through the gather map (integer sums, exact), decoding, CRC24A, transport-block bits.
-//                 Block index = local_alloc * n_sf + subframe.
-template <int NT, bool FUSED>
+template <int NT, int MODE>
 __global__ void __launch_bounds__(NT / 2 < 32 ? 32 : NT / 2, NT == 384 ? 2 : (NT == 192 ? 4 : (NT == 128 ? 6 : 12)))
-turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16_t *__restrict__ piT2g, uint8_t *__restrict__ out,
+turbo_mlm2_kernel(const void *__restrict__ in, int K, int n_iter, const uint16_t *__restrict__ piT2g, uint8_t *__restrict__ out,
                   const __grid_constant__ FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -255,120 +271,40 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
     constexpr int NT2 = NT / 2, NP = WIN * NT;
     __shared__ float s_red[32];
     __shared__ int s_tail[12];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int cb = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
     const int n_thr = K / (2 * WIN);                     // active threads: one per pair of windows (K is a multiple of 32)
     const bool active = t < n_thr;
     const int k0 = 2 * WIN * t;                          // first trellis step of window 2t; window 2t+1 starts at k0 + 16
 
-    float m = 0.f;
-    float tail_v = 0.f;
-    if (FUSED) {
-        const int a_loc = cb / fp.n_sf, sf = cb - a_loc * fp.n_sf;
-        const FusedAlloc &A = fp.al[a_loc];
-        const int sn = fp.subfr_num[sf];
-        const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
-        const int M = A.M[cls], E = M * A.Qm;
-        // staging: soft bits (int8, E <= 112 NT bytes) over S1 | piT2 | Ls | Lp1 | Lp2; un-matched sums (int16 [3][NP]) over recA | recB | acc
-        int8_t *soft = reinterpret_cast<int8_t *>(sm.S1);
-        int16_t *Y = reinterpret_cast<int16_t *>(smem_raw);
-        const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
-        const int *ix = A.re_idx + cls * A.idx_stride;
-        const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
-        const int Qm = A.Qm, mod = A.mod;
-        auto emit = [&](int r, float xr, float xi) { emit_soft(xr, xi, mod, Qm, cs + r * Qm, soft + r * Qm); };
-        if (fp.N_ant != 1) {
-            // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
-            const size_t ps = (size_t)14 * fp.nsc;
-            for (int r = t * fp.N_ant; r < M; r += nt * fp.N_ant) {
-                if (fp.N_ant == 2) {
-                    float2 x0, x1;
-                    sfbc2(gr[ix[r]], gr[ix[r + 1]], ch[ix[r]], ch[ps + ix[r]], x0, x1);
-                    emit(r, x0.x, x0.y); emit(r + 1, x1.x, x1.y);
-                } else {
-                    const float2 y[4] = {gr[ix[r]], gr[ix[r + 1]], gr[ix[r + 2]], gr[ix[r + 3]]};
-                    float2 x[4];
-                    sfbc4(y, ch[ix[r]], ch[ps + ix[r + 2]], ch[2 * ps + ix[r]], ch[3 * ps + ix[r + 2]], x);
-                    for (int q = 0; q < 4; q++) emit(r + q, x[q].x, x[q].y);
-                }
-            }
-        } else {
-            // every thread handles RE_IT resource elements per round; indices, grid and estimate values are all fetched before the
-            // arithmetic starts, so the global-memory latency is paid once per round, not per element
-            constexpr int RE_IT = 8;
-            for (int r0 = t; r0 < M; r0 += RE_IT * nt) {
-                int idx[RE_IT];
-                float2 yv[RE_IT], hv[RE_IT];
-#pragma unroll
-                for (int u = 0; u < RE_IT; u++) idx[u] = (r0 + u * nt < M) ? ix[r0 + u * nt] : ix[r0];
-#pragma unroll
-                for (int u = 0; u < RE_IT; u++) { yv[u] = gr[idx[u]]; hv[u] = ch[idx[u]]; }
-#pragma unroll
-                for (int u = 0; u < RE_IT; u++) {
-                    const int r = r0 + u * nt;
-                    if (r < M) {
-                        float xr, xi;
-                        zf_1port(yv[u], hv[u], xr, xi);
-                        emit(r, xr, xi);
-                    }
-                }
-            }
+    if (MODE == MODE_Q8) {
+        // ---- input: two bulk copies (LLR image of this block, interleaver table) land while the threads clear the exchange state
+        constexpr uint32_t IMG = 3 * NP + 16, TAB = 2 * NP;
+        if (t == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, IMG + TAB);
+            bulk_copy_g2s(sm.Ls, static_cast<const int8_t *>(in) + (size_t)cb * IMG, IMG, &s_bar);
+            bulk_copy_g2s(sm.piT2, piT2g, TAB, &s_bar);
         }
-        __syncthreads();
-        // rate unmatching (liblte_phy.cc:11403-11415): the first visit assigns, repeats are added in visiting order.  The reference works in
-        // float with the sentinel 10000 for "nothing received"; the soft bits are small integers, so integer sums are exact and the
-        // sentinel comparisons are restated on the integers (a running sum that hits 10000 exactly is replaced, as there).
-        constexpr int NUL = 10000;
-        const int period = A.period;
-        const bool two_visits = E <= 2 * period;          // every output is visited at most twice: v = x0 + x1, no sentinel can arise
-        auto unmatch = [&](int fk) -> int {
-            if (two_visits) {
-                const int k1 = fk + period;
-                const int x0 = (fk >= 0 && fk < E) ? soft[fk] : 0, x1 = (fk >= 0 && k1 < E) ? soft[k1] : 0;
-                return x0 + x1;
-            }
-            int w = NUL;
-            if (fk >= 0)
-#pragma unroll 1
-                for (int k = fk; k < E; k += period) {
-                    const int x = soft[k];
-                    w = (w == NUL) ? x : w + x;
-                }
-            return w == NUL ? 0 : w;                       // turbo_decode zeroes the sentinels (liblte_phy.cc:10636-10642)
-        };
-        int mi = 0;
+        for (int p = t; p < NP; p += nt) sm.acc[p] = 0;
+        for (int p = t; p < 2 * (NT2 + 1) * 2; p += nt) {
+            (&sm.recA[0][0][0])[p] = make_uint4(0, 0, 0, 0);
+            (&sm.recB[0][0][0])[p] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();                                    // the barrier object is initialised before anybody polls it
+        mbar_wait(&s_bar, 0);
         if (active) {
-            uint32_t *Y32 = reinterpret_cast<uint32_t *>(Y) + t;
-            // gather map of the thread's 2 x 48 outputs: vector loads, all in flight before the first shared-memory walk
-            const int4 *fA4 = reinterpret_cast<const int4 *>(A.first_k + 3 * k0), *fB4 = fA4 + 3 * WIN / 4;
+            const uint16_t *Ls16 = reinterpret_cast<const uint16_t *>(sm.Ls) + t;
+            uint32_t *S1w = reinterpret_cast<uint32_t *>(sm.S1) + t;
 #pragma unroll
-            for (int c = 0; c < 2; c++) {                   // 8 steps of both windows per round
-                int fa[24], fb[24];
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const int4 u = fA4[6 * c + j], v = fB4[6 * c + j];
-                    fa[4 * j] = u.x; fa[4 * j + 1] = u.y; fa[4 * j + 2] = u.z; fa[4 * j + 3] = u.w;
-                    fb[4 * j] = v.x; fb[4 * j + 1] = v.y; fb[4 * j + 2] = v.z; fb[4 * j + 3] = v.w;
-                }
-#pragma unroll
-                for (int ii = 0; ii < 8; ii++) {
-                    const int i = 8 * c + ii;
-#pragma unroll
-                    for (int x = 0; x < 3; x++) {
-                        const int vA = unmatch(fa[3 * ii + x]), vB = unmatch(fb[3 * ii + x]);
-                        mi = max(mi, max(abs(vA), abs(vB)));
-                        Y32[(x * NP + i * NT) / 2] = pk(vA, vB);
-                    }
-                }
-            }
+            for (int i = 0; i < WIN; i++) S1w[i * NT2] = s8x2_to_s16x2(Ls16[i * NT2]);     // Le1 = 0: S1 = Lsys
         }
-        int tail_i = 0;
-        if (t < 12) { tail_i = unmatch(A.first_k[3 * K + t]); mi = max(mi, abs(tail_i)); }
-        m = (float)mi;
-        tail_v = (float)tail_i;
+        if (t < 12) s_tail[t] = sm.tail8[t];
     } else {
         // ---- input, first pass: max |d| over all 3(K+4) inputs (sentinel -> 0).  Thread t owns 96 consecutive floats (384 B).
-        const float *d = llr + (size_t)cb * 3 * (K + 4);
+        const float *d = static_cast<const float *>(in) + (size_t)cb * 3 * (K + 4);
+        float m = 0.f, tail_v = 0.f;
         if (active) {
             const float4 *src = reinterpret_cast<const float4 *>(d + 3 * k0);
 #pragma unroll 6
@@ -386,61 +322,27 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
             if (tail_v == LTEB200_RX_NULL_BIT) tail_v = 0.f;
             m = fmaxf(m, fabsf(tail_v));
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((t & 31) == 0) s_red[t >> 5] = m;
-    __syncthreads();                                        // also: soft[] is dead, Y[] is complete
-    if (t < 32) {
-        float v = t < (nt >> 5) ? s_red[t] : 0.f;
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (t == 0) s_red[0] = v;
-    }
-    __syncthreads();
-    const float maxv = s_red[0];
-    // Fused path: the un-matched values are integers with |v| <= maxv, so the reference's quantisation q(v) = trunc(v * 127 / maxv)
-    // (liblte_phy.cc:10645-10664, IEEE multiply and divide) is tabulated once per block for 0..maxv (q is odd) instead of dividing
-    // 18,444 times; the table sits in the (not yet staged) interleaver-table area.  Larger ranges divide directly.
-    int8_t *lut = reinterpret_cast<int8_t *>(sm.piT2);
-    const int maxi = FUSED ? (int)maxv : 0;
-    const bool use_lut = FUSED && maxi < 2 * NP;
-    if (FUSED) {
-        if (use_lut) for (int p = t; p <= maxi; p += nt) lut[p] = (int8_t)qf((float)p, maxv);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((t & 31) == 0) s_red[t >> 5] = m;
         __syncthreads();
-    }
-    auto q_int = [&](int v) -> int {
-        if (use_lut) { const int q = lut[abs(v)]; return v < 0 ? -q : q; }
-        return qf((float)v, maxv);
-    };
-    // ---- quantise into the window-transposed arrays: thread t writes the (2t, 2t+1) word of every row
-    if (active) {
-        uint16_t *Ls16 = reinterpret_cast<uint16_t *>(sm.Ls) + t, *Lp116 = reinterpret_cast<uint16_t *>(sm.Lp1) + t, *Lp216 = reinterpret_cast<uint16_t *>(sm.Lp2) + t;
-        uint32_t *S1w = reinterpret_cast<uint32_t *>(sm.S1) + t;
-        if (FUSED) {
-            const uint32_t *Y32 = reinterpret_cast<const uint32_t *>(smem_raw) + t;
-            uint32_t y[3][WIN];
-#pragma unroll
-            for (int x = 0; x < 3; x++)
-#pragma unroll
-                for (int i = 0; i < WIN; i++) y[x][i] = Y32[(x * NP + i * NT) / 2];
-            // every thread's own Y words are in registers now; S1 / Ls / Lp alias the (dead) soft bits, not Y
-#pragma unroll
-            for (int i = 0; i < WIN; i++) {
-                const int sA = q_int(lo16(y[0][i])), sB = q_int(hi16(y[0][i]));
-                const int pA = q_int(lo16(y[1][i])), pB = q_int(hi16(y[1][i]));
-                const int rA = q_int(lo16(y[2][i])), rB = q_int(hi16(y[2][i]));
-                Ls16[i * NT2] = (uint16_t)((sA & 0xff) | ((sB & 0xff) << 8));
-                Lp116[i * NT2] = (uint16_t)((pA & 0xff) | ((pB & 0xff) << 8));
-                Lp216[i * NT2] = (uint16_t)((rA & 0xff) | ((rB & 0xff) << 8));
-                S1w[i * NT2] = pk(sA, sB);
-            }
-        } else {
-            const float *d = llr + (size_t)cb * 3 * (K + 4) + 3 * k0;
+        if (t < 32) {
+            float v = t < (nt >> 5) ? s_red[t] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (t == 0) s_red[0] = v;
+        }
+        __syncthreads();
+        const float maxv = s_red[0];
+        // ---- second pass: quantise into the window-transposed arrays, thread t writes the (2t, 2t+1) word of every row
+        if (active) {
+            uint16_t *Ls16 = reinterpret_cast<uint16_t *>(sm.Ls) + t, *Lp116 = reinterpret_cast<uint16_t *>(sm.Lp1) + t, *Lp216 = reinterpret_cast<uint16_t *>(sm.Lp2) + t;
+            uint32_t *S1w = reinterpret_cast<uint32_t *>(sm.S1) + t;
+            const float *dw = d + 3 * k0;
 #pragma unroll
             for (int c = 0; c < WIN / 4; c++) {              // 4 steps of both windows per round: 12 + 12 floats
                 float va[12], vb[12];
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    const float4 x = reinterpret_cast<const float4 *>(d + 12 * c)[j], y = reinterpret_cast<const float4 *>(d + 3 * WIN + 12 * c)[j];
+                    const float4 x = reinterpret_cast<const float4 *>(dw + 12 * c)[j], y = reinterpret_cast<const float4 *>(dw + 3 * WIN + 12 * c)[j];
                     va[4 * j] = x.x; va[4 * j + 1] = x.y; va[4 * j + 2] = x.z; va[4 * j + 3] = x.w;
                     vb[4 * j] = y.x; vb[4 * j + 1] = y.y; vb[4 * j + 2] = y.z; vb[4 * j + 3] = y.w;
                 }
@@ -462,15 +364,14 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
                 }
             }
         }
-    }
-    if (t < 12) s_tail[t] = qf(tail_v, maxv);                // s_tail[3*r + x] = q(d_x[K+r])
-    if (FUSED) __syncthreads();                             // Y[] (over recA | recB | acc) and the quantisation table are dead from here on
-    // ---- interleaver table, accumulators, boundary records
-    for (int p = t; p < NP / 2; p += nt) reinterpret_cast<uint32_t *>(sm.piT2)[p] = reinterpret_cast<const uint32_t *>(piT2g)[p];
-    for (int p = t; p < NP; p += nt) sm.acc[p] = 0;
-    for (int p = t; p < 2 * (NT2 + 1) * 2; p += nt) {
-        (&sm.recA[0][0][0])[p] = make_uint4(0, 0, 0, 0);
-        (&sm.recB[0][0][0])[p] = make_uint4(0, 0, 0, 0);
+        if (t < 12) s_tail[t] = qf(tail_v, maxv);            // s_tail[3*r + x] = q(d_x[K+r])
+        // ---- interleaver table, accumulators, boundary records
+        for (int p = t; p < NP / 2; p += nt) reinterpret_cast<uint32_t *>(sm.piT2)[p] = reinterpret_cast<const uint32_t *>(piT2g)[p];
+        for (int p = t; p < NP; p += nt) sm.acc[p] = 0;
+        for (int p = t; p < 2 * (NT2 + 1) * 2; p += nt) {
+            (&sm.recA[0][0][0])[p] = make_uint4(0, 0, 0, 0);
+            (&sm.recB[0][0][0])[p] = make_uint4(0, 0, 0, 0);
+        }
     }
     __syncthreads();
     if (t < 2) {
@@ -542,7 +443,7 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
             if (hi16(s) + clampi(la.y, -LA_LIM, LA_LIM) < 0) bits |= 1u << (WIN + i);
         }
     }
-    if (!FUSED) {
+    if (MODE == MODE_F32) {
         if (active) {
             // one byte per bit, 32 consecutive bytes
             uint32_t w[8];
@@ -600,13 +501,16 @@ turbo_mlm2_kernel(const float *__restrict__ llr, int K, int n_iter, const uint16
 
 }  // namespace
 
-// soft-bit capacity of the fused kernel's staging area for a block size (bytes = soft bits), see Smem / the FUSED input phase
-int mlm2_fused_capacity(int K) { return 112 * mlm_size_class(K); }
 bool mlm2_handles(int K) { return K >= 64 && (K & 31) == 0 && getenv("LTEB200_MLM_V1") == nullptr; }
+size_t mlm2_q8_stride(int K) { return (size_t)3 * WIN * mlm_size_class(K) + 16; }
 
-int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused, cudaStream_t stream)
+// q8 == nullptr: float LLRs d_llr[n_cb][3(K+4)] in, decoded bits d_bits[n_cb][K] out.
+// q8 != nullptr: quantised images in (mlm2_q8_stride(K) bytes per block), transport blocks + CRC verdicts out as `fused` describes.
+int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, const int8_t *q8, int K, int n_cb, int n_iter, uint8_t *d_bits, const FusedParams *fused,
+                      cudaStream_t stream)
 {
     if (!mlm2_handles(K) || K > 6144) { lteb200_set_error(ctx, "turbo (pair kernel): K=%d is not a multiple of 32", K); return LTEB200_ERR_ARGS; }
+    if ((q8 != nullptr) != (fused != nullptr)) { lteb200_set_error(ctx, "turbo (pair kernel): inconsistent input/output mode"); return LTEB200_ERR_ARGS; }
     if (n_iter < 1) n_iter = 1;
     QppTables qt;
     int rc = lteb200_get_qpp(ctx, K, &qt);  // validates K
@@ -631,15 +535,16 @@ int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int
     FusedParams none;
     memset(&none, 0, sizeof(none));
     const FusedParams &fp = fused ? *fused : none;
-#define MLM2_LAUNCH(NT_, FUSED_)                                                                                                        \
-    do {                                                                                                                                \
-        const size_t smem = sizeof(Smem<NT_>);                                                                                          \
-        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm2_kernel<NT_, FUSED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm2_kernel<NT_, FUSED_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
-        turbo_mlm2_kernel<NT_, FUSED_><<<n_cb, threads, smem, stream>>>(d_llr, K, n_iter, piT2, d_bits, fp);                            \
+    const void *in = q8 ? (const void *)q8 : (const void *)d_llr;
+#define MLM2_LAUNCH(NT_, MODE_)                                                                                                        \
+    do {                                                                                                                               \
+        const size_t smem = sizeof(Smem<NT_>);                                                                                         \
+        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm2_kernel<NT_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LTE_CUDA_OK(ctx, cudaFuncSetAttribute(turbo_mlm2_kernel<NT_, MODE_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
+        turbo_mlm2_kernel<NT_, MODE_><<<n_cb, threads, smem, stream>>>(in, K, n_iter, piT2, d_bits, fp);                               \
     } while (0)
-    if (fused) { if (NT == 64) MLM2_LAUNCH(64, true); else if (NT == 128) MLM2_LAUNCH(128, true); else if (NT == 192) MLM2_LAUNCH(192, true); else MLM2_LAUNCH(384, true); }
-    else       { if (NT == 64) MLM2_LAUNCH(64, false); else if (NT == 128) MLM2_LAUNCH(128, false); else if (NT == 192) MLM2_LAUNCH(192, false); else MLM2_LAUNCH(384, false); }
+    if (q8) { if (NT == 64) MLM2_LAUNCH(64, MODE_Q8); else if (NT == 128) MLM2_LAUNCH(128, MODE_Q8); else if (NT == 192) MLM2_LAUNCH(192, MODE_Q8); else MLM2_LAUNCH(384, MODE_Q8); }
+    else    { if (NT == 64) MLM2_LAUNCH(64, MODE_F32); else if (NT == 128) MLM2_LAUNCH(128, MODE_F32); else if (NT == 192) MLM2_LAUNCH(192, MODE_F32); else MLM2_LAUNCH(384, MODE_F32); }
 #undef MLM2_LAUNCH
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
