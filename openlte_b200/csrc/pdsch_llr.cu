@@ -31,7 +31,7 @@ __device__ __noinline__ void emit_soft(float xr, float xi, int mod, int Qm, cons
         if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
 }
 
-constexpr int LUT_MAX = 2048;     // |v| range that is tabulated (127 x 16 repeats); beyond it the division is done per value
+constexpr int LUT_MAX = 4096;     // table of q over -max..max (127 x 16 repeats each way); beyond it the division is done per value
 
 // first_kT: gather map in OUTPUT order: [x][pos] for the three streams (pos = (k mod 16) * NT + k / 16, -1 on the padding) followed by the 12
 // tail entries d[3K + j].  q8 image per block: Ls[NP] | Lp1[NP] | Lp2[NP] | tail[16].
@@ -114,8 +114,16 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
     // ---- pass 1: max |v| over the 3 K + 12 outputs (padding entries are -1 -> 0)
     const int NP = 16 * NT, n_map = 3 * NP + 12;
     const int *fkT = A.first_kT;
+    const int n2 = E > period ? E - period : 0;        // e-bits [0, n2) are visited a second time at [period, period + n2)
     int mi = 0;
-    for (int j = t; j < n_map; j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
+    if (two_visits) {
+        // the first-lap e-bits [0, period) are in one-to-one correspondence with the outputs that receive anything, so the maximum over
+        // the outputs is a maximum over e-bits: no index loads
+        const int n1 = E < period ? E : period;
+        for (int k = t; k < n1; k += THREADS) mi = max(mi, abs((int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)));
+    } else {
+        for (int j = t; j < n_map; j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
+    }
     for (int o = 16; o > 0; o >>= 1) mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
     if ((t & 31) == 0) s_red[t >> 5] = mi;
     __syncthreads();
@@ -127,17 +135,30 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
     __syncthreads();
     const int maxi = s_red[0];
     const float maxv = (float)maxi;
-    const bool use_lut = maxi < LUT_MAX;
-    if (use_lut) for (int p = t; p <= maxi; p += THREADS) lut[p] = (int8_t)qf((float)p, maxv);
+    // q(v) tabulated over -maxi..maxi (index v + maxi)
+    const bool use_lut = 2 * maxi < LUT_MAX;
+    if (use_lut) for (int p = t; p <= 2 * maxi; p += THREADS) lut[p] = (int8_t)qf((float)(p - maxi), maxv);
     __syncthreads();
-    auto q_int = [&](int v) -> uint32_t {
-        int q;
-        if (use_lut) { q = lut[abs(v)]; q = v < 0 ? -q : q; } else q = qf((float)v, maxv);
-        return (uint32_t)q & 0xffu;
-    };
     // ---- pass 2: quantised image, four consecutive output bytes per thread and round
     int8_t *img = q8 + (size_t)cb * (3 * NP + 16);
     const int4 *fk4 = reinterpret_cast<const int4 *>(fkT);
+    if (two_visits && use_lut) {
+        const int8_t *lutc = lut + maxi;
+        auto q2 = [&](int fk) -> uint32_t {
+            const int x0 = (unsigned)fk < (unsigned)E ? (int)soft[fk] : 0, x1 = (unsigned)fk < (unsigned)n2 ? (int)soft[fk + period] : 0;
+            return (uint32_t)(uint8_t)lutc[x0 + x1];
+        };
+        for (int j = t; j < 3 * NP / 4; j += THREADS) {
+            const int4 f = fk4[j];
+            reinterpret_cast<uint32_t *>(img)[j] = q2(f.x) | (q2(f.y) << 8) | (q2(f.z) << 16) | (q2(f.w) << 24);
+        }
+        if (t < 16) img[3 * NP + t] = t < 12 ? (int8_t)q2(fkT[3 * NP + t]) : (int8_t)0;
+        return;
+    }
+    auto q_int = [&](int v) -> uint32_t {
+        const int q = use_lut ? (int)lut[v + maxi] : qf((float)v, maxv);
+        return (uint32_t)q & 0xffu;
+    };
     for (int j = t; j < 3 * NP / 4; j += THREADS) {
         const int4 f = fk4[j];
         const uint32_t w = q_int(unmatch(f.x)) | (q_int(unmatch(f.y)) << 8) | (q_int(unmatch(f.z)) << 16) | (q_int(unmatch(f.w)) << 24);

@@ -119,6 +119,7 @@ struct Smem {
     // recB[d][n_threads] = the termination vector in its lo lanes
     uint4 recA[2][NT2 + 1][2];
     uint4 recB[2][NT2 + 1][2];
+    uint4 scr[6][NT2];      // per-thread stash of the inputs of steps 0..7 and the start metrics while steps 15..8 run backward
     int acc[NP];            // sum of the second decoder's extrinsics per natural position (a-priori of the first decoder, unclamped)
     int16_t S1[NP];         // Lsys + Le1 (natural order): a-priori + systematic of the second decoder, read through pi
     uint16_t piT2[NP];      // 2 * position of pi(k), stored at the position of k (byte offset into S1)
@@ -126,85 +127,120 @@ struct Smem {
     int8_t tail8[16];                   // q(d_x[K + r]) at [3 r + x], 12 used
 };
 
+// Inputs of steps i0..i0+7 of both windows: (Lsa_lo, Lsa_hi) and (Lp_lo, Lp_hi) per step; 24 independent shared-memory loads.
+//   first decoder : Lsa = Lsys + clamp(accumulated extrinsics of the second decoder); the accumulator is cleared for the next scatter
+//   second decoder: Lsa = S1[pi] (= Lsys + Le1 at the interleaved position), one random 16-bit read per window
 template <int NT, bool SECOND>
-__device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool active, uint32_t (&a_in)[8], uint32_t (&b)[8], const int n_thr)
+__device__ __forceinline__ void load_inputs(Smem<NT> &sm, const int t, const int i0, uint32_t (&ls)[8], uint32_t (&lp)[8])
+{
+    constexpr int NT2 = NT / 2;
+    const uint16_t *Lp16 = reinterpret_cast<const uint16_t *>(SECOND ? sm.Lp2 : sm.Lp1) + t + i0 * NT2;
+    if (SECOND) {
+        const uint32_t *pi32 = reinterpret_cast<const uint32_t *>(sm.piT2) + t + i0 * NT2;
+        const char *s1 = reinterpret_cast<const char *>(sm.S1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t q2 = pi32[i * NT2];
+            const int vA = *reinterpret_cast<const int16_t *>(s1 + (q2 & 0xffffu));
+            const int vB = *reinterpret_cast<const int16_t *>(s1 + (q2 >> 16));
+            ls[i] = pk(vA, vB);
+            lp[i] = s8x2_to_s16x2(Lp16[i * NT2]);
+        }
+    } else {
+        const uint16_t *Ls16 = reinterpret_cast<const uint16_t *>(sm.Ls) + t + i0 * NT2;
+        int2 *acc2 = reinterpret_cast<int2 *>(sm.acc) + t + i0 * NT2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int2 s = acc2[i * NT2];
+            acc2[i * NT2] = make_int2(0, 0);
+            const uint32_t la = pk(clampi(s.x, -LA_LIM, LA_LIM), clampi(s.y, -LA_LIM, LA_LIM));
+            ls[i] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), la);
+            lp[i] = s8x2_to_s16x2(Lp16[i * NT2]);
+        }
+    }
+}
+// keeps the compiler from moving memory operations across a phase boundary (hoisted loads lengthen live ranges and end in spills)
+__device__ __forceinline__ void phase_fence() { asm volatile("" ::: "memory"); }
+
+template <int NT, bool SECOND>
+__device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool active, uint32_t (&a_in)[8], uint32_t (&b)[8])
 {
     constexpr int NT2 = NT / 2;
     constexpr int D = SECOND ? 1 : 0;
     if (active) {
-        // ---- inputs of the 16 steps, both windows: (Lsa_lo, Lsa_hi) and (Lp_lo, Lp_hi) per step.  Independent loads, issued up front.
-        uint32_t in_ls[WIN], in_lp[WIN];
-        const uint16_t *Lp16 = reinterpret_cast<const uint16_t *>(SECOND ? sm.Lp2 : sm.Lp1) + t;
-        if (SECOND) {
-            const uint32_t *pi32 = reinterpret_cast<const uint32_t *>(sm.piT2) + t;
-            const char *s1 = reinterpret_cast<const char *>(sm.S1);
+        uint4 *scr = &sm.scr[0][t];                           // private stash: [6][NT2] x 16 B, conflict free
+        uint32_t a[8], A[8][8];
+        uint32_t hi_ls[8], hi_lp[8];                          // inputs of steps 8..15, live from their prefetch to their backward step
+        {
+            uint32_t in_ls[8], in_lp[8];
+            load_inputs<NT, SECOND>(sm, t, 0, in_ls, in_lp);
+            // The inputs of steps 0..7 and the window's start metrics are needed again only after the backward recursion over steps
+            // 15..8: they wait in shared memory meanwhile, which keeps the peak register demand (64 stored forward metrics + 8 backward
+            // metrics + the inputs of 8 steps) under the 168 registers that two blocks per SM allow -- the first version spilled 30
+            // registers per pass to local memory and spent a fifth of the pass waiting for them (profiles/r2_pair_kernel_ncu.json).
+            scr[0 * NT2] = make_uint4(in_ls[0], in_ls[1], in_ls[2], in_ls[3]);
+            scr[1 * NT2] = make_uint4(in_ls[4], in_ls[5], in_ls[6], in_ls[7]);
+            scr[2 * NT2] = make_uint4(in_lp[0], in_lp[1], in_lp[2], in_lp[3]);
+            scr[3 * NT2] = make_uint4(in_lp[4], in_lp[5], in_lp[6], in_lp[7]);
+            scr[4 * NT2] = make_uint4(a_in[0], a_in[1], a_in[2], a_in[3]);
+            scr[5 * NT2] = make_uint4(a_in[4], a_in[5], a_in[6], a_in[7]);
 #pragma unroll
-            for (int i = 0; i < WIN; i++) {
-                const uint32_t q2 = pi32[i * NT2];
-                const int vA = *reinterpret_cast<const int16_t *>(s1 + (q2 & 0xffffu));
-                const int vB = *reinterpret_cast<const int16_t *>(s1 + (q2 >> 16));
-                in_ls[i] = pk(vA, vB);
-                in_lp[i] = s8x2_to_s16x2(Lp16[i * NT2]);
-            }
-        } else {
-            const uint16_t *Ls16 = reinterpret_cast<const uint16_t *>(sm.Ls) + t;
-            int2 *acc2 = reinterpret_cast<int2 *>(sm.acc) + t;
+            for (int s = 0; s < 8; s++) a[s] = a_in[s];
+            // ---- forward over steps 0..7 (nothing kept)
 #pragma unroll
-            for (int i = 0; i < WIN; i++) {
-                const int2 s = acc2[i * NT2];
-                acc2[i * NT2] = make_int2(0, 0);                   // cleared for the next iteration's scatter
-                const uint32_t la = pk(clampi(s.x, -LA_LIM, LA_LIM), clampi(s.y, -LA_LIM, LA_LIM));
-                in_ls[i] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), la);
-                in_lp[i] = s8x2_to_s16x2(Lp16[i * NT2]);
+            for (int i = 0; i < 8; i++) {
+                if ((i & 3) == 0) fwd_step<true>(a, in_ls[i], in_lp[i]); else fwd_step<false>(a, in_ls[i], in_lp[i]);
             }
         }
-        uint32_t a[8], A[8][8];
+        phase_fence();
+        load_inputs<NT, SECOND>(sm, t, 8, hi_ls, hi_lp);
+        // ---- forward over steps 8..15, the metrics at the start of each step stay in registers
 #pragma unroll
-        for (int s = 0; s < 8; s++) a[s] = a_in[s];
-        // ---- forward over the whole window; the metrics of steps 8..15 stay in registers
+        for (int i = 0; i < 8; i++) {
 #pragma unroll
-        for (int i = 0; i < WIN; i++) {
-            if (i >= 8) {
-#pragma unroll
-                for (int s = 0; s < 8; s++) A[i - 8][s] = a[s];
-            }
-            if ((i & 3) == 0) fwd_step<true>(a, in_ls[i], in_lp[i]); else fwd_step<false>(a, in_ls[i], in_lp[i]);
+            for (int s = 0; s < 8; s++) A[i][s] = a[s];
+            if ((i & 3) == 0) fwd_step<true>(a, hi_ls[i], hi_lp[i]); else fwd_step<false>(a, hi_ls[i], hi_lp[i]);
         }
         sm.recA[D][1 + t][0] = make_uint4(a[0], a[1], a[2], a[3]);
         sm.recA[D][1 + t][1] = make_uint4(a[4], a[5], a[6], a[7]);
-        // ---- backward over steps 15..8, then the forward metrics of steps 0..7 are recomputed and consumed
         const uint16_t *Ls16 = reinterpret_cast<const uint16_t *>(sm.Ls) + t;
         uint32_t *S1w = reinterpret_cast<uint32_t *>(sm.S1) + t;
         const uint32_t *pi32 = reinterpret_cast<const uint32_t *>(sm.piT2) + t;
         char *accb = reinterpret_cast<char *>(sm.acc);
-#pragma unroll
-        for (int half = 1; half >= 0; half--) {
-            if (half == 0) {
-#pragma unroll
-                for (int s = 0; s < 8; s++) a[s] = a_in[s];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-#pragma unroll
-                    for (int s = 0; s < 8; s++) A[i][s] = a[s];
-                    if (i < 7) { if ((i & 3) == 0) fwd_step<true>(a, in_ls[i], in_lp[i]); else fwd_step<false>(a, in_ls[i], in_lp[i]); }
-                }
+        // backward step i of both windows + extrinsic output
+        auto back = [&](const int i, const uint32_t (&al)[8], const uint32_t ls, const uint32_t lp) {
+            uint32_t d2;
+            if ((i & 3) == 3) d2 = bwd_step<true>(b, al, ls, lp); else d2 = bwd_step<false>(b, al, ls, lp);
+            d2 = vsub(d2, ls);
+            const int eA = ext_of(lo16(d2)), eB = ext_of(hi16(d2));
+            if (SECOND) {
+                const uint32_t q2 = pi32[i * NT2];
+                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 & 0xffffu)), eA);
+                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 >> 16)), eB);
+            } else {
+                S1w[i * NT2] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), pk(eA, eB));
             }
+        };
+        // ---- backward over steps 15..8
 #pragma unroll
-            for (int j = 7; j >= 0; j--) {
-                const int i = 8 * half + j;
-                uint32_t d2;
-                if ((i & 3) == 3) d2 = bwd_step<true>(b, A[j], in_ls[i], in_lp[i]); else d2 = bwd_step<false>(b, A[j], in_ls[i], in_lp[i]);
-                d2 = vsub(d2, in_ls[i]);
-                const int eA = ext_of(lo16(d2)), eB = ext_of(hi16(d2));
-                if (SECOND) {
-                    const uint32_t q2 = pi32[i * NT2];
-                    atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 & 0xffffu)), eA);
-                    atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 >> 16)), eB);
-                } else {
-                    S1w[i * NT2] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), pk(eA, eB));
-                }
-            }
+        for (int j = 7; j >= 0; j--) back(8 + j, A[j], hi_ls[j], hi_lp[j]);
+        phase_fence();
+        // ---- forward metrics of steps 0..7 again, from the stashed start metrics and inputs; then backward over steps 7..0
+        uint32_t lo_ls[8], lo_lp[8];
+        {
+            const uint4 v0 = scr[0 * NT2], v1 = scr[1 * NT2], v2 = scr[2 * NT2], v3 = scr[3 * NT2], v4 = scr[4 * NT2], v5 = scr[5 * NT2];
+            lo_ls[0] = v0.x; lo_ls[1] = v0.y; lo_ls[2] = v0.z; lo_ls[3] = v0.w; lo_ls[4] = v1.x; lo_ls[5] = v1.y; lo_ls[6] = v1.z; lo_ls[7] = v1.w;
+            lo_lp[0] = v2.x; lo_lp[1] = v2.y; lo_lp[2] = v2.z; lo_lp[3] = v2.w; lo_lp[4] = v3.x; lo_lp[5] = v3.y; lo_lp[6] = v3.z; lo_lp[7] = v3.w;
+            a[0] = v4.x; a[1] = v4.y; a[2] = v4.z; a[3] = v4.w; a[4] = v5.x; a[5] = v5.y; a[6] = v5.z; a[7] = v5.w;
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) A[i][s] = a[s];
+            if (i < 7) { if ((i & 3) == 0) fwd_step<true>(a, lo_ls[i], lo_lp[i]); else fwd_step<false>(a, lo_ls[i], lo_lp[i]); }
+        }
+#pragma unroll
+        for (int j = 7; j >= 0; j--) back(j, A[j], lo_ls[j], lo_lp[j]);
         sm.recB[D][t][0] = make_uint4(b[0], b[1], b[2], b[3]);
         sm.recB[D][t][1] = make_uint4(b[4], b[5], b[6], b[7]);
         // ---- boundary metrics of the NEXT pass (the other decoder): nobody writes that decoder's records before the barrier below
@@ -224,7 +260,6 @@ __device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool a
             b[6] = __byte_perm(o1.z, n1.z, 0x5432); b[7] = __byte_perm(o1.w, n1.w, 0x5432);
         }
     }
-    (void)n_thr;
     __syncthreads();
 }
 
@@ -426,8 +461,8 @@ turbo_mlm2_kernel(const void *__restrict__ in, int K, int n_iter, const uint16_t
     __syncthreads();
 
     for (int it = 0; it < n_iter; it++) {
-        dec_pass<NT, false>(sm, t, active, a_in, b, n_thr);
-        dec_pass<NT, true>(sm, t, active, a_in, b, n_thr);
+        dec_pass<NT, false>(sm, t, active, a_in, b);
+        dec_pass<NT, true>(sm, t, active, a_in, b);
     }
 
     // ---- decisions of the thread's 32 steps: bit = (Lsys + Le1 + La1 < 0)
