@@ -52,6 +52,11 @@ def turbo_decode_mlm(d, n_iter=8):
     out = np.zeros(K, np.uint8); lib().op_turbo_decode_mlm(_p(d), K, n_iter, _p(out)); return out
 
 
+def turbo_decode_mlm_float(d, n_iter=8):
+    d = np.ascontiguousarray(d, np.float32); K = d.size // 3 - 4
+    out = np.zeros(K, np.uint8); lib().op_turbo_decode_mlm_float(_p(d), K, n_iter, _p(out)); return out
+
+
 def siso(a, b):
     a = np.ascontiguousarray(a, np.int8); b = np.ascontiguousarray(b, np.int8)
     out = np.zeros(a.size, np.int8); lib().op_siso(_p(a), _p(b), int(a.size), _p(out)); return out

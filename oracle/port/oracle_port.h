@@ -30,6 +30,8 @@ void op_siso(const int8_t *a, const int8_t *b, int K, int8_t *act);    /* viterb
 /* ---- max-log-MAP ("mode B"; no reference counterpart): restated so that the CUDA kernel has a
  *      bit-exact CPU twin.  See port/turbo_mlm.cc for the numeric definition. */
 void op_turbo_decode_mlm(const float *d, int K, int n_iter, uint8_t *out);
+/* independent float, full-block (non-windowed) max-log-MAP: bounds the loss of the windowed int16 definition (port/turbo_mlm_float.cc) */
+void op_turbo_decode_mlm_float(const float *d, int K, int n_iter, uint8_t *out);
 
 /* ---- rate unmatching (a13) */
 int  op_rate_unmatch_turbo(const float *e, int E, int D /*K+4*/, int C, int tx_mode, int N_soft, int M_dl_harq,
