@@ -11,17 +11,33 @@
 //   liblte_phy_code_block_segmentation / _desegmentation :1337-1362
 //   turbo_decode -- liblte/src/liblte_phy.cc:1530-1535 (file-local prototype, external linkage) and the new
 //   public alias liblte_phy_turbo_decode BASELINE.json names.
-// Not provided (still the reference's CPU code for a caller that needs them):
-//   liblte_phy_bch_channel_decode, liblte_phy_pdcch_channel_decode.
+//   liblte_phy_bch_channel_decode :947-953 / liblte_phy_pdcch_channel_decode :1012-1020 (N_ant == 1 for the PDCCH, see lte_b200.h)
 //
 // Types keep the reference's names and field names so callers compile unchanged; LIBLTE_PHY_STRUCT keeps only the
 // public "Generic" fields callers read (phy_struct->N_samps_per_subfr, ->fs, LTE_fdd_dl_fs_samp_buf.cc:194,707) plus
 // an opaque handle to the device context -- the reference's 46 MB of host scratch has no counterpart here.
+//
+// Use next to the reference's other headers.  Every real caller also includes liblte_rrc.h / liblte_common.h / typedefs.h
+// (LTE_fdd_dl_fs_samp_buf.h:55-56).  When those headers are on the include path this file takes the fixed-width typedefs,
+// LIBLTE_ERROR_ENUM, LIBLTE_BIT_MSG_STRUCT and the RRC enums FROM THEM and adds only what liblte_phy.h would have declared;
+// include/dropin/liblte_phy.h is a one-line forwarder, so that `-Iinclude/dropin` in front of the reference's liblte/hdr makes
+// the caller's own `#include "liblte_phy.h"` pick this surface (tests/test_fs_scan_gpu.py builds the reference's
+// LTE_fdd_dl_fs_samp_buf.cc that way and runs its work() on the shipped capture).  Without them it is self-contained.
 #ifndef LIBLTE_PHY_B200_H
 #define LIBLTE_PHY_B200_H
 
 #include <stdint.h>
 
+#if defined(__has_include)
+#if __has_include("liblte_common.h") && __has_include("liblte_rrc.h") && !defined(LIBLTE_PHY_B200_STANDALONE)
+#define LIBLTE_PHY_B200_REFERENCE_TYPES 1
+#endif
+#endif
+
+#ifdef LIBLTE_PHY_B200_REFERENCE_TYPES
+#include "liblte_common.h"   // typedefs.h (int8 is plain char there: callers must keep -fsigned-char semantics), LIBLTE_ERROR_ENUM, LIBLTE_BIT_MSG_STRUCT
+#include "liblte_rrc.h"      // LIBLTE_RRC_PHICH_DURATION_ENUM, liblte_rrc_phich_resource_num, ...
+#else
 typedef signed char        int8;      // the reference's plain `char` is signed on x86 only: fixed here
 typedef unsigned char      uint8;
 typedef short              int16;
@@ -40,7 +56,10 @@ typedef enum {
     LIBLTE_ERROR_INVALID_CONTENTS,
 } LIBLTE_ERROR_ENUM;
 typedef struct { uint32 N_bits; uint8 msg[LIBLTE_MAX_MSG_SIZE]; } LIBLTE_BIT_MSG_STRUCT;
+typedef enum { LIBLTE_RRC_PHICH_DURATION_NORMAL = 0, LIBLTE_RRC_PHICH_DURATION_EXTENDED } LIBLTE_RRC_PHICH_DURATION_ENUM;
+#endif
 
+// ---- what liblte_phy.h declares on this path (liblte_phy.h:100-224)
 #define LIBLTE_PHY_N_RB_DL_1_4MHZ 6
 #define LIBLTE_PHY_N_RB_DL_3MHZ   15
 #define LIBLTE_PHY_N_RB_DL_5MHZ   25
@@ -54,8 +73,25 @@ typedef struct { uint32 N_bits; uint8 msg[LIBLTE_MAX_MSG_SIZE]; } LIBLTE_BIT_MSG
 #define LIBLTE_PHY_MAX_CODE_BLOCK_SIZE 6176
 #define LIBLTE_PHY_INIT_N_ID_CELL_UNKNOWN 0xFFFF
 #define LIBLTE_PHY_N_MAX_ROUGH_CORR_SEARCH_PEAKS 5
+// samples per frame / subframe / slot at each sample rate (liblte_phy.h:141-175): callers size their buffers with these
+#define LIBLTE_PHY_N_SAMPS_PER_SLOT_30_72MHZ  15360
+#define LIBLTE_PHY_N_SAMPS_PER_SUBFR_30_72MHZ (LIBLTE_PHY_N_SAMPS_PER_SLOT_30_72MHZ*2)
+#define LIBLTE_PHY_N_SAMPS_PER_FRAME_30_72MHZ (LIBLTE_PHY_N_SAMPS_PER_SUBFR_30_72MHZ*10)
+#define LIBLTE_PHY_N_SAMPS_PER_SLOT_15_36MHZ  7680
+#define LIBLTE_PHY_N_SAMPS_PER_SUBFR_15_36MHZ (LIBLTE_PHY_N_SAMPS_PER_SLOT_15_36MHZ*2)
+#define LIBLTE_PHY_N_SAMPS_PER_FRAME_15_36MHZ (LIBLTE_PHY_N_SAMPS_PER_SUBFR_15_36MHZ*10)
+#define LIBLTE_PHY_N_SAMPS_PER_SLOT_7_68MHZ   3840
+#define LIBLTE_PHY_N_SAMPS_PER_SUBFR_7_68MHZ  (LIBLTE_PHY_N_SAMPS_PER_SLOT_7_68MHZ*2)
+#define LIBLTE_PHY_N_SAMPS_PER_FRAME_7_68MHZ  (LIBLTE_PHY_N_SAMPS_PER_SUBFR_7_68MHZ*10)
+#define LIBLTE_PHY_N_SAMPS_PER_SLOT_3_84MHZ   1920
+#define LIBLTE_PHY_N_SAMPS_PER_SUBFR_3_84MHZ  (LIBLTE_PHY_N_SAMPS_PER_SLOT_3_84MHZ*2)
+#define LIBLTE_PHY_N_SAMPS_PER_FRAME_3_84MHZ  (LIBLTE_PHY_N_SAMPS_PER_SUBFR_3_84MHZ*10)
+#define LIBLTE_PHY_N_SAMPS_PER_SLOT_1_92MHZ   960
+#define LIBLTE_PHY_N_SAMPS_PER_SUBFR_1_92MHZ  (LIBLTE_PHY_N_SAMPS_PER_SLOT_1_92MHZ*2)
+#define LIBLTE_PHY_N_SAMPS_PER_FRAME_1_92MHZ  (LIBLTE_PHY_N_SAMPS_PER_SUBFR_1_92MHZ*10)
 
 typedef enum { LIBLTE_PHY_FS_1_92MHZ = 0, LIBLTE_PHY_FS_3_84MHZ, LIBLTE_PHY_FS_7_68MHZ, LIBLTE_PHY_FS_15_36MHZ, LIBLTE_PHY_FS_30_72MHZ, LIBLTE_PHY_FS_N_ITEMS } LIBLTE_PHY_FS_ENUM;
+static const char liblte_phy_fs_text[LIBLTE_PHY_FS_N_ITEMS][20] = {"1.92", "3.84", "7.68", "15.36", "30.72"};   // liblte_phy.h:206-210
 typedef enum { LIBLTE_PHY_PRE_CODER_TYPE_TX_DIVERSITY = 0, LIBLTE_PHY_PRE_CODER_TYPE_SPATIAL_MULTIPLEXING } LIBLTE_PHY_PRE_CODER_TYPE_ENUM;
 typedef enum { LIBLTE_PHY_MODULATION_TYPE_BPSK = 0, LIBLTE_PHY_MODULATION_TYPE_QPSK, LIBLTE_PHY_MODULATION_TYPE_16QAM, LIBLTE_PHY_MODULATION_TYPE_64QAM } LIBLTE_PHY_MODULATION_TYPE_ENUM;
 typedef enum { LIBLTE_PHY_CHAN_TYPE_DLSCH = 0, LIBLTE_PHY_CHAN_TYPE_PCH, LIBLTE_PHY_CHAN_TYPE_ULSCH, LIBLTE_PHY_CHAN_TYPE_ULCCH } LIBLTE_PHY_CHAN_TYPE_ENUM;
@@ -138,7 +174,6 @@ LIBLTE_ERROR_ENUM liblte_phy_pdsch_channel_decode(LIBLTE_PHY_STRUCT *phy_struct,
                                                   uint8 *out_bits, uint32 *N_out_bits);
 // ---- control channels (liblte_phy.h:941-947, 967-1013)
 #define LIBLTE_PHY_PDCCH_MAX_ALLOC 6
-typedef enum { LIBLTE_RRC_PHICH_DURATION_NORMAL = 0, LIBLTE_RRC_PHICH_DURATION_EXTENDED } LIBLTE_RRC_PHICH_DURATION_ENUM;
 typedef struct { LIBLTE_PHY_ALLOCATION_STRUCT alloc[LIBLTE_PHY_PDCCH_MAX_ALLOC]; uint32 N_symbs; uint32 N_alloc; } LIBLTE_PHY_PDCCH_STRUCT;
 typedef struct { float n[4]; uint32 k[4]; uint32 cfi; uint32 N_reg; } LIBLTE_PHY_PCFICH_STRUCT;
 typedef struct { float z_re[3]; float z_im[3]; uint32 k[75]; uint32 N_reg; uint8 b[25][8]; bool present[25][8]; } LIBLTE_PHY_PHICH_STRUCT;
