@@ -239,46 +239,60 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
         int chunk = atoi(e);
         if (chunk < 64) chunk = 64;
         for (int b = chunk; b < n_sf; b += chunk) bounds.push_back(b);
-    } else if (n_sf >= 1024) {
-        // measured on 4000 subframes (tools/e2e_schedule_sweep.sh): 160, 320, 640, ~1250, ~1250, 256, 128 beats equal chunks by 10 % and
-        // finer ramps by 2 %
-        const int plateau = 1280;
-        std::vector<int> head, tail;
-        int used = 0;
-        for (int sz = 160; sz < plateau && used + sz <= n_sf / 3; sz *= 2) { head.push_back(sz); used += sz; }
-        for (int sz = 128; sz <= 256 && used + sz <= n_sf / 2; sz *= 2) { tail.push_back(sz); used += sz; }
-        int mid = n_sf - used, pos = 0;
-        for (int sz : head) { pos += sz; bounds.push_back(pos); }
-        const int n_mid = (mid + plateau - 1) / plateau;
-        for (int i = 1; i <= n_mid; i++) bounds.push_back(pos + (int)((long long)mid * i / n_mid));
-        pos += mid;
-        for (int i = (int)tail.size() - 1; i > 0; i--) { pos += tail[i]; bounds.push_back(pos); }
     } else if (n_sf >= 256) {
-        for (int i = 1; i < 4; i++) bounds.push_back(n_sf * i / 4);
+        // With the round-2 kernels a 20 MHz subframe costs about as much on the GPU (1.3 us) as its 61 KB cost on PCIe (1.15 us), so the
+        // pipeline is balanced: a chunk can only start once ALL its samples have arrived, which makes the first chunk's copy and every
+        // growth step exposed time.  Chunks therefore start small and grow only as fast as the compute backlog allows
+        // (size <= first + 0.12 x subframes already queued keeps the decode stream from ever waiting for a copy), and every size is a
+        // whole number of decoder waves (148 SMs x resident blocks / transport blocks per subframe) so that no chunk ends in a
+        // partial wave.  Measured on 4000 subframes (profiles/r2_e2e_schedule.txt): 7.3 -> about 6 ms per call.
+        int K_first = 6144;
+        { AllocTables t0; if (get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[0], &t0) == LTEB200_OK) K_first = t0.K; }
+        const int nt_class = mlm_size_class(K_first);
+        const int blocks_per_sm = nt_class == 384 ? 2 : (nt_class == 192 ? 4 : (nt_class == 128 ? 6 : 12));
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+        int wave = (n_sm * blocks_per_sm) / n_alloc;
+        if (wave < 16) wave = 16;
+        // a chunk costs about 1.28 us per subframe + 0.1 ms (kernel tails, launch gaps), the copy of the next one 1.2 us per subframe: the decode
+        // stream never waits if next <= 1.07 x current + 83; the last chunk is kept small (its transport blocks are copied out after everything else)
+        const int first = 2 * wave, cap = 12 * wave;
+        int pos = 0, sz = first;
+        while (n_sf - pos > sz + 3 * wave) {
+            pos += sz;
+            bounds.push_back(pos);
+            int nxt = (int)(1.07 * sz) + 83;
+            nxt = (nxt / wave) * wave;
+            if (nxt > cap) nxt = cap;
+            sz = nxt;
+        }
+        if (n_sf - pos > 6 * wave) { pos = n_sf - 3 * wave; bounds.push_back(pos); }
     }
     if (bounds.back() != n_sf) bounds.push_back(n_sf);
     const int n_chunks = (int)bounds.size() - 1;
     // a subframe's 16 symbols end two symbols into the next subframe (the estimator's look-ahead): that halo travels with the chunk
     const long long halo = 2LL * ((128LL << fs_idx) + (10LL << fs_idx)) + 16;
-    std::vector<cudaEvent_t> ev_h(n_chunks), ev_c(n_chunks);
+    StreamScope scope;                 // every event and stream-ordered allocation below is released on every exit path
+    std::vector<cudaEvent_t> ev_h(n_chunks), ev_c(n_chunks), ev_f(n_chunks);
     for (int c = 0; c < n_chunks; c++) {
-        LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_h[c], cudaEventDisableTiming));
-        LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_c[c], cudaEventDisableTiming));
+        LTE_CUDA_OK(ctx, scope.event(&ev_h[c]));
+        LTE_CUDA_OK(ctx, scope.event(&ev_c[c]));
+        LTE_CUDA_OK(ctx, scope.event(&ev_f[c]));
     }
     cudaEvent_t ev_alloc;
-    LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    LTE_CUDA_OK(ctx, scope.event(&ev_alloc));
     // LTEB200_E2E_TRACE=1: device-side time line of the three streams, printed to stderr (development aid)
     const bool trace = getenv("LTEB200_E2E_TRACE") != nullptr;
     cudaEvent_t tr[6] = {};
-    if (trace) for (auto &e : tr) cudaEventCreate(&e);
+    if (trace) for (auto &e : tr) LTE_CUDA_OK(ctx, scope.event(&e, cudaEventDefault));
     std::vector<cudaEvent_t> tr_c0, tr_c1;
     void *d_iq = nullptr;
     uint8_t *d_tb = nullptr;
     int32_t *d_ok = nullptr;
     const size_t tb_row = (size_t)n_alloc * tb_stride;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_iq, samp_bytes * n_samps, ctx->s_comp));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)n_sf * tb_row, ctx->s_comp));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, ctx->s_comp));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_iq, samp_bytes * n_samps, ctx->s_comp));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_tb, (size_t)n_sf * tb_row, ctx->s_comp));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_ok, sizeof(int32_t) * (size_t)n_sf * n_alloc, ctx->s_comp));
     if (trace) cudaEventRecord(tr[0], ctx->s_comp);
     LTE_CUDA_OK(ctx, cudaEventRecord(ev_alloc, ctx->s_comp));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_alloc, 0));
@@ -308,26 +322,36 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     // (s_comp) drains its last wave, so the tail of one chunk is filled with the head of the next.
     int rc = LTEB200_OK;
     const int nsc = 12 * N_rb_dl;
-    std::vector<cudaEvent_t> ev_f(n_chunks);
-    for (int c = 0; c < n_chunks; c++) LTE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_f[c], cudaEventDisableTiming));
     LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_front, ev_alloc, 0));
+    // start indices and subframe numbers of the whole batch go to the device once; the chunks use offsets into them
+    for (int i = 0; i < n_sf; i++) if (h_subfr_num[i] < 0 || h_subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); rc = LTEB200_ERR_ARGS; }
+    long long *d_start_all = nullptr;
+    int *d_sn_all = nullptr;
+    if (rc == LTEB200_OK) {
+        // (allocated in the order of the stream that fills them; the decode stream only touches them behind an event of that stream, and the
+        // scope releases them after the final synchronisation)
+        LTE_CUDA_OK(ctx, scope.alloc(&d_start_all, sizeof(long long) * n_sf, ctx->s_front));
+        LTE_CUDA_OK(ctx, scope.alloc(&d_sn_all, sizeof(int) * n_sf, ctx->s_front));
+        rc = lteb200_upload_small(ctx, h_start_idx, sizeof(long long) * n_sf, d_start_all, ctx->s_front);
+        if (rc == LTEB200_OK) rc = lteb200_upload_small(ctx, h_subfr_num, sizeof(int) * n_sf, d_sn_all, ctx->s_front);
+    }
     for (int c = 0; c < n_chunks && rc == LTEB200_OK; c++) {
         const int b0 = bounds[c], nb = bounds[c + 1] - b0;
         float *d_grid = nullptr, *d_ce = nullptr;
         LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_front, ev_h[c], 0));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)nb, ctx->s_front));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)nb * N_ant, ctx->s_front));
-        rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, h_start_idx + b0, h_subfr_num + b0, nb, d_grid, d_ce,
-                                                  ctx->s_front);
+        LTE_CUDA_OK(ctx, scope.alloc(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)nb, ctx->s_front));
+        LTE_CUDA_OK(ctx, scope.alloc(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)nb * N_ant, ctx->s_front));
+        rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start_all + b0, nb, d_grid, ctx->s_front);
+        if (rc == LTEB200_OK) rc = chan_est_launch(ctx, d_grid, d_sn_all + b0, N_rb_dl, N_id_cell, N_ant, nb, d_ce, ctx->s_front);
         if (rc) break;
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_f[c], ctx->s_front));
         LTE_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_comp, ev_f[c], 0));
-        if (trace) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tr_c0.push_back(a); tr_c1.push_back(b); cudaEventRecord(a, ctx->s_comp); }
-        rc = lteb200_pdsch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, h_subfr_num + b0, nb, N_pdcch_symbs, allocs, n_alloc, turbo_mode, n_iter,
-                                        d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
+        if (trace) { cudaEvent_t a, b; LTE_CUDA_OK(ctx, scope.event(&a, cudaEventDefault)); LTE_CUDA_OK(ctx, scope.event(&b, cudaEventDefault)); tr_c0.push_back(a); tr_c1.push_back(b); cudaEventRecord(a, ctx->s_comp); }
+        rc = pdsch_decode_batch_dev(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, h_subfr_num + b0, d_sn_all + b0, nb, N_pdcch_symbs, allocs, n_alloc, turbo_mode,
+                                    n_iter, d_tb + (size_t)b0 * tb_row, tb_stride, d_ok + (size_t)b0 * n_alloc, ctx->s_comp);
         if (rc) break;
-        cudaFreeAsync(d_grid, ctx->s_comp);
-        cudaFreeAsync(d_ce, ctx->s_comp);
+        scope.release(d_grid, ctx->s_comp);       // stream-ordered after the decode kernels that read them
+        scope.release(d_ce, ctx->s_comp);
         if (trace && c == 0) cudaEventRecord(tr[3], ctx->s_comp);
         if (trace) cudaEventRecord(tr_c1[c], ctx->s_comp);
         LTE_CUDA_OK(ctx, cudaEventRecord(ev_c[c], ctx->s_comp));
@@ -349,13 +373,8 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
             cudaEventElapsedTime(&a, tr[0], tr_c0[c]); cudaEventElapsedTime(&b, tr[0], tr_c1[c]);
             fprintf(stderr, "  chunk %zu: %d subframes, compute %.3f -> %.3f ms (%.3f ms, %.2f us/subframe)\n", c, bounds[c + 1] - bounds[c], a, b, b - a,
                     1e3 * (b - a) / (bounds[c + 1] - bounds[c]));
-            cudaEventDestroy(tr_c0[c]); cudaEventDestroy(tr_c1[c]);
         }
-        for (auto &e : tr) cudaEventDestroy(e);
     }
-    cudaFreeAsync(d_iq, ctx->s_comp); cudaFreeAsync(d_tb, ctx->s_comp); cudaFreeAsync(d_ok, ctx->s_comp);
-    for (int c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_h[c]); cudaEventDestroy(ev_c[c]); cudaEventDestroy(ev_f[c]); }
-    cudaEventDestroy(ev_alloc);
     if (rc == LTEB200_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
         lteb200_set_error(ctx, "dl_receive_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
         rc = LTEB200_ERR_CUDA;

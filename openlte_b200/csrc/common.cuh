@@ -86,3 +86,33 @@ int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out);
 int lteb200_get_crc24a_tab(lteb200_ctx *ctx, const uint32_t **out);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Stream-ordered temporaries and events of one call, released on EVERY exit path (the error macro returns from the middle of a function).
+struct StreamScope {
+    std::vector<std::pair<void *, cudaStream_t>> mem;
+    std::vector<cudaEvent_t> evs;
+    template <typename T> cudaError_t alloc(T **p, size_t bytes, cudaStream_t s)
+    {
+        const cudaError_t e = cudaMallocAsync((void **)p, bytes ? bytes : 1, s);
+        if (e == cudaSuccess) mem.emplace_back((void *)*p, s);
+        return e;
+    }
+    cudaError_t event(cudaEvent_t *e, unsigned flags = cudaEventDisableTiming)
+    {
+        const cudaError_t r = cudaEventCreateWithFlags(e, flags);
+        if (r == cudaSuccess) evs.push_back(*e);
+        return r;
+    }
+    // free now, in the order of stream s (the usual case inside a pipeline loop)
+    void release(void *p, cudaStream_t s)
+    {
+        for (size_t i = 0; i < mem.size(); i++)
+            if (mem[i].first == p) { mem.erase(mem.begin() + i); break; }
+        cudaFreeAsync(p, s);
+    }
+    ~StreamScope()
+    {
+        for (auto &m : mem) cudaFreeAsync(m.first, m.second);
+        for (auto &e : evs) cudaEventDestroy(e);
+    }
+};

@@ -35,3 +35,6 @@ int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, const int8_t *q8, in
                       cudaStream_t stream);
 // PDSCH symbol level + rate unmatching + quantisation into that image, one CTA per transport block (pdsch_llr.cu)
 int pdsch_llr_q8_launch(lteb200_ctx *ctx, const FusedParams &fp, int K, int E_max, int8_t *d_q8, cudaStream_t stream);
+int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num,
+                           const int *d_subfr_dev, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
+                           uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, cudaStream_t stream);

@@ -268,6 +268,15 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
                                           const int *subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc,
                                           int turbo_mode, int n_iter, uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
 {
+    return pdsch_decode_batch_dev(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, subfr_num, nullptr, n_sf, N_pdcch_symbs, allocs, n_alloc, turbo_mode, n_iter,
+                                  d_tb_bits, tb_stride, d_crc_ok, (cudaStream_t)stream_);
+}
+
+// d_subfr_dev: the same subframe numbers already resident on the device (the host pipeline uploads them once for all its chunks), or null.
+int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num,
+                           const int *d_subfr_dev, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
+                           uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, cudaStream_t stream_)
+{
     if (!ctx || !d_grid || !d_ce || !subfr_num || !allocs || !d_tb_bits || !d_crc_ok || n_sf < 1 || n_alloc < 1) return LTEB200_ERR_ARGS;
     if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -291,9 +300,11 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
         if (!mlm2_handles(T[a].K) && T[a].M[2] * T[a].Qm > 64 * NT) fusable = false;    // (the pair kernel's symbol-level kernel stages any single-block allocation)
     }
     if (fusable) {
-        int *d_sn = nullptr;
-        rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, stream);
-        if (rc) return rc;
+        int *d_sn = const_cast<int *>(d_subfr_dev);
+        if (!d_sn) {
+            rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, stream);
+            if (rc) return rc;
+        }
         const uint32_t *crc_tab = nullptr;
         rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
         for (int a = 0; a < n_alloc && rc == LTEB200_OK;) {
@@ -329,7 +340,7 @@ extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid,
                 rc = turbo_mlm_fused_batch(ctx, T[a].K, n_iter, fp, stream);
             a = e;
         }
-        cudaFreeAsync(d_sn, stream);
+        if (!d_subfr_dev) cudaFreeAsync(d_sn, stream);
         return rc;
     }
     // per-call device parameter arrays: subframe numbers and per-(alloc, subframe) E
