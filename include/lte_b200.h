@@ -122,6 +122,21 @@ int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const floa
                                int N_ant, const int *subfr_num /* HOST */, int n_sf, int N_pdcch_symbs,
                                const lteb200_alloc *allocs /* HOST */, int n_alloc, int turbo_mode, int n_iter,
                                uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream);
+/* The two halves of the max-log-MAP receive path as separate calls (what lteb200_pdsch_decode_batch runs back to back when every block size is a
+ * multiple of 32).  All allocations of one call share one code block size K; at most 8 allocations.
+ *   lteb200_pdsch_llr_q8_batch : RE extraction (liblte_phy.cc:3745-3802), ZF / transmit-diversity combining (:7645-7796), demapping (:9502-9660),
+ *       descrambling (:3831-3836), rate unmatching (:11246-11490) and the quantisation at the head of turbo_decode (:10636-10664), one CTA per transport
+ *       block.  d_q8: DEVICE, one int8 image per (allocation, subframe) at index a * n_sf + subframe, lteb200_q8_stride(K) bytes each:
+ *       Lsys | Lpar1 | Lpar2 in the decoder's window-transposed order, then the 12 tail values.
+ *   lteb200_turbo_decode_q8_batch : n_iter iterations of max-log-MAP on those images, then CRC24A and transport-block extraction
+ *       (dlsch_channel_decode's tail, liblte_phy.cc:12841-12869); outputs as lteb200_pdsch_decode_batch. */
+size_t lteb200_q8_stride(int K);   /* 0 if K is not handled by this path (not a multiple of 32) */
+int lteb200_pdsch_llr_q8_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
+                               const int *subfr_num /* HOST */, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs /* HOST */, int n_alloc,
+                               int8_t *d_q8, void *stream);
+int lteb200_turbo_decode_q8_batch(lteb200_ctx *ctx, const int8_t *d_q8, int K, int n_cb /* = n_alloc * n_sf */, int n_iter,
+                                  const lteb200_alloc *allocs /* HOST */, int n_alloc, int n_sf, uint8_t *d_tb_bits, int tb_stride,
+                                  int32_t *d_crc_ok, void *stream);
 /* Host twin of liblte_phy_pdsch_channel_decode for one allocation; returns LTEB200_ERR_DECODE on CRC failure and
  * leaves out_bits / N_out_bits untouched in that case, like the reference. */
 int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *rx_symb_re, const float *rx_symb_im,

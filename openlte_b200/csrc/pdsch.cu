@@ -264,6 +264,92 @@ extern "C" int lteb200_pdsch_demod_batch(lteb200_ctx *ctx, const float *d_grid, 
 }
 
 // Full PDSCH receive of a batch, all allocations.  Scratch layout per allocation a: soft [n_sf][G_stride], d [n_sf][3(K+4)], cb [n_sf][K].
+// Per-allocation part of the receive parameters for allocations [a, e) of equal block size (at most 8 per group)
+static int fill_group(lteb200_ctx *ctx, const std::vector<AllocTables> &T, const lteb200_alloc *allocs, int n_alloc, int a, int *e_out, FusedParams &fp)
+{
+    int e = a;
+    while (e < n_alloc && e - a < 8 && T[e].K == T[a].K) {
+        RateUnmatchMap m;
+        int rc = rate_unmatch_get_map(ctx, T[e].K + 4, 0, 1, allocs[e].tx_mode, 250368, 8, 0, allocs[e].rv_idx, &m);   // M_dl_harq 8, cat-1 N_soft: liblte_phy.cc:3843-3844
+        if (rc) return rc;
+        FusedAlloc &A = fp.al[e - a];
+        A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.first_k = m.first_k; A.first_kT = m.first_kT; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
+        for (int c = 0; c < 3; c++) A.M[c] = T[e].M[c];
+        A.Qm = T[e].Qm; A.mod = allocs[e].mod_type; A.period = m.n_nonnull; A.F = T[e].F; A.tbs = allocs[e].tbs; A.a_idx = e;
+        e++;
+    }
+    fp.n_al = e - a;
+    *e_out = e;
+    return LTEB200_OK;
+}
+
+// The two halves of the max-log-MAP receive path as separate entry points (all allocations of one call must share the block size K, K mod 32 == 0,
+// at most 8 allocations): the symbol level writes one quantised image per (allocation, subframe), index a * n_sf + subframe, lteb200_q8_stride(K) bytes
+// each; the decoder turns images into transport blocks + CRC verdicts.
+extern "C" size_t lteb200_q8_stride(int K) { return mlm2_handles(K) ? mlm2_q8_stride(K) : 0; }
+
+static int q8_common(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, std::vector<AllocTables> &T,
+                     FusedParams &fp)
+{
+    if (n_alloc < 1 || n_alloc > 8) { lteb200_set_error(ctx, "q8 path: 1..8 allocations per call"); return LTEB200_ERR_ARGS; }
+    T.resize(n_alloc);
+    for (int a = 0; a < n_alloc; a++) {
+        int rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[a], &T[a]);
+        if (rc) return rc;
+        if (T[a].K != T[0].K || !mlm2_handles(T[a].K)) { lteb200_set_error(ctx, "q8 path: allocations must share one block size that is a multiple of 32"); return LTEB200_ERR_UNSUPPORTED; }
+        for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant) { lteb200_set_error(ctx, "allocation is not a whole number of transmit-diversity groups"); return LTEB200_ERR_UNSUPPORTED; }
+    }
+    memset(&fp, 0, sizeof(fp));
+    int e = 0;
+    int rc = fill_group(ctx, T, allocs, n_alloc, 0, &e, fp);
+    if (rc) return rc;
+    if (e != n_alloc) return LTEB200_ERR_UNSUPPORTED;
+    fp.N_ant = N_ant; fp.nsc = 12 * N_rb_dl; fp.n_alloc_total = n_alloc;
+    return LTEB200_OK;
+}
+
+extern "C" int lteb200_pdsch_llr_q8_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num,
+                                          int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int8_t *d_q8, void *stream_)
+{
+    if (!ctx || !d_grid || !d_ce || !subfr_num || !allocs || !d_q8 || n_sf < 1) return LTEB200_ERR_ARGS;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); return LTEB200_ERR_ARGS; }
+    std::vector<AllocTables> T;
+    FusedParams fp;
+    int rc = q8_common(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs, n_alloc, T, fp);
+    if (rc) return rc;
+    StreamScope scope;
+    int *d_sn = nullptr;
+    LTE_CUDA_OK(ctx, scope.alloc(&d_sn, sizeof(int) * n_sf, stream));
+    if ((rc = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream))) return rc;
+    fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.n_sf = n_sf;
+    int E_max = 0;
+    for (int a = 0; a < n_alloc; a++) E_max = std::max(E_max, T[a].M[2] * T[a].Qm);
+    return pdsch_llr_q8_launch(ctx, fp, T[0].K, E_max, d_q8, stream);
+}
+
+extern "C" int lteb200_turbo_decode_q8_batch(lteb200_ctx *ctx, const int8_t *d_q8, int K, int n_cb, int n_iter, const lteb200_alloc *allocs, int n_alloc, int n_sf,
+                                             uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
+{
+    if (!ctx || !d_q8 || !allocs || !d_tb_bits || !d_crc_ok || n_sf < 1 || n_alloc < 1 || n_alloc > 8 || n_cb != n_alloc * n_sf) return LTEB200_ERR_ARGS;
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (!mlm2_handles(K)) { lteb200_set_error(ctx, "q8 decoder: K=%d is not a multiple of 32", K); return LTEB200_ERR_UNSUPPORTED; }
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    for (int a = 0; a < n_alloc; a++) {
+        int Ka = 0, Fa = 0;
+        if (seg_params(allocs[a].tbs, &Ka, &Fa) || Ka != K) { lteb200_set_error(ctx, "q8 decoder: transport block size %d does not map onto K=%d", allocs[a].tbs, K); return LTEB200_ERR_ARGS; }
+        if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+        fp.al[a].F = Fa; fp.al[a].tbs = allocs[a].tbs; fp.al[a].a_idx = a;
+    }
+    const uint32_t *crc_tab = nullptr;
+    int rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
+    if (rc) return rc;
+    fp.crc_tab = crc_tab; fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride; fp.n_al = n_alloc;
+    return turbo_mlm2_launch(ctx, nullptr, d_q8, K, n_cb, n_iter, nullptr, &fp, (cudaStream_t)stream_);
+}
+
 extern "C" int lteb200_pdsch_decode_batch(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant,
                                           const int *subfr_num, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc,
                                           int turbo_mode, int n_iter, uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, void *stream_)
@@ -314,19 +400,8 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
             fp.N_ant = N_ant;
             fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
             int e = a;
-            while (e < n_alloc && e - a < 8 && T[e].K == T[a].K) {
-                RateUnmatchMap m;
-                rc = rate_unmatch_get_map(ctx, T[e].K + 4, 0, 1, allocs[e].tx_mode, 250368, 8, 0, allocs[e].rv_idx, &m);
-                if (rc) break;
-                FusedAlloc &A = fp.al[e - a];
-                A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.first_k = m.first_k; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
-                for (int c = 0; c < 3; c++) A.M[c] = T[e].M[c];
-                A.first_kT = m.first_kT;
-                A.Qm = T[e].Qm; A.mod = allocs[e].mod_type; A.period = m.n_nonnull; A.F = T[e].F; A.tbs = allocs[e].tbs; A.a_idx = e;
-                e++;
-            }
+            rc = fill_group(ctx, T, allocs, n_alloc, a, &e, fp);
             if (rc) break;
-            fp.n_al = e - a;
             if (mlm2_handles(T[a].K)) {
                 // symbol level -> quantised LLR images (18 KB per K = 6144 block), then the pair-lane decoder with CRC + transport-block output
                 int E_max = 0;

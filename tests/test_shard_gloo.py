@@ -65,3 +65,49 @@ def test_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GATHER_OK" in r.stdout
+
+
+WORKER2 = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    from openlte_b200 import shard, sharded
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_sf, fs_idx, first = 11, 0, 7
+    halo = shard.halo_samples(fs_idx)
+    stream = None
+    if rank == 0:
+        rng = np.random.default_rng(1)
+        stream = torch.from_numpy(rng.integers(-100, 100, (n_sf * 1920 + halo, 2)).astype(np.int8))
+    def decode(iq_local, starts, sn):      # stand-in for the receive chain: per-subframe checksum over the subframe AND its halo, tagged with the subframe number
+        tb = torch.zeros((len(starts), 2, 4), dtype=torch.uint8); ok = torch.zeros((len(starts), 2), dtype=torch.int32)
+        for i, s in enumerate(starts):
+            c = int(iq_local[s:s + 1920 + halo].to(torch.int64).sum())
+            tb[i, 0] = torch.tensor([(c >> (8 * k)) & 255 for k in range(4)], dtype=torch.uint8)
+            tb[i, 1, 0] = sn[i]
+            ok[i] = torch.tensor([1, sn[i]])
+        return tb, ok
+    for mode in ("broadcast", "scatter"):
+        tb, ok = sharded.receive_sharded(stream, dict(n_sf=n_sf, first_subfr=first, fs_idx=fs_idx) if rank == 0 else None, decode, (2, 4), "cpu", distribute=mode)
+        if rank == 0:
+            want_tb, want_ok = decode(stream, [i * 1920 for i in range(n_sf)], shard.subframe_numbers(first, 0, n_sf))
+            assert torch.equal(tb, want_tb) and torch.equal(ok, want_ok), mode
+    if rank == 0:
+        print("SHARDED_OK")
+    dist.destroy_process_group()
+""")
+
+
+def test_receive_sharded_world_size_2_gloo(tmp_path):
+    """openlte_b200/sharded.py (parameter broadcast, stream broadcast / scatter with halo, gather in stream order) equals the single-process result."""
+    script = tmp_path / "worker2.py"
+    script.write_text(WORKER2 % ROOT)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "SHARDED_OK" in r.stdout
