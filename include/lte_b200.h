@@ -270,6 +270,14 @@ int lteb200_freq_shift(lteb200_ctx *ctx, float *i_buf, float *q_buf, uint32_t st
 /* Fused form: the OFDM demodulator applies the shift while loading samples (no extra pass over the data). */
 int lteb200_set_freq_offset(lteb200_ctx *ctx, float freq_offset_hz, long long index_base);
 
+/* Demapper of the max-log-MAP receive path (lteb200_pdsch_decode_batch / dl_receive_* / dl_scan_batch with LTEB200_TURBO_MAXLOGMAP, and
+ * lteb200_pdsch_llr_q8_batch).  REFERENCE (default): the reference's own equaliser and demapper, bit for bit -- zero forcing, QPSK soft by distance,
+ * hard +-127 decisions for 16/64QAM (liblte_phy.cc:7680-7690, :9502-9660).  MAXLOG: the north-star soft path -- noise variance from the CRS,
+ * per-RE MMSE weighting (|h|^2 / sigma^2) and exact max-log LLRs per bit (int8: round(2 LLR), +-127); one antenna port or transmit diversity
+ * with proper maximum-ratio normalisation.  Block sizes that are not a multiple of 32 and the reference-exact decoder keep the reference demapper. */
+enum { LTEB200_DEMAP_REFERENCE = 0, LTEB200_DEMAP_MAXLOG = 1 };
+int lteb200_set_demapper(lteb200_ctx *ctx, int demap);
+
 /* --------------------------------------------------------------------------------------------- utilities */
 /* Pseudo-random sequence c(n), generate_prs_c (liblte_phy.cc:9669-9704); d_c DEVICE [len] bytes. */
 int lteb200_prs_c_batch(lteb200_ctx *ctx, uint32_t c_init, int len, uint8_t *d_c, void *stream);

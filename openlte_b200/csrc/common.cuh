@@ -52,6 +52,7 @@ struct lteb200_ctx {
     cudaStream_t s_h2d, s_comp, s_d2h, s_front;   // pipeline streams of the host-pointer entry point (lazily created)
     float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)
     long long    cfo_base;
+    int          demap;        // LTEB200_DEMAP_* for the max-log-MAP receive path
     // pinned, device-mapped ring for small per-call parameter arrays (see lteb200_upload_small)
     char        *ring_h, *ring_d;
     size_t       ring_bytes, ring_off;

@@ -36,6 +36,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->crc24a_tab = nullptr;
     c->ring_h = c->ring_d = nullptr; c->ring_bytes = c->ring_off = 0;
     c->cfo_hz = 0.f; c->cfo_base = 0;
+    c->demap = LTEB200_DEMAP_REFERENCE;
     c->s_h2d = c->s_comp = c->s_d2h = c->s_front = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
@@ -63,6 +64,13 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     for (auto &kv : c->mlm2) cudaFree(kv.second);
     for (auto &kv : c->rum) { cudaFree(kv.second.first_k); cudaFree(kv.second.first_kT); }
     delete c;
+}
+
+extern "C" int lteb200_set_demapper(lteb200_ctx *c, int demap)
+{
+    if (!c || (demap != LTEB200_DEMAP_REFERENCE && demap != LTEB200_DEMAP_MAXLOG)) return LTEB200_ERR_ARGS;
+    c->demap = demap;
+    return LTEB200_OK;
 }
 
 extern "C" const char *lteb200_last_error(lteb200_ctx *c) { return c ? c->last_error.c_str() : "null context"; }

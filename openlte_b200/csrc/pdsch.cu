@@ -305,6 +305,7 @@ static int q8_common(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
     if (rc) return rc;
     if (e != n_alloc) return LTEB200_ERR_UNSUPPORTED;
     fp.N_ant = N_ant; fp.nsc = 12 * N_rb_dl; fp.n_alloc_total = n_alloc;
+    fp.demap = ctx->demap; fp.vshift = N_id_cell % 6;
     return LTEB200_OK;
 }
 
@@ -398,6 +399,7 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
             memset(&fp, 0, sizeof(fp));
             fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.crc_tab = crc_tab;
             fp.N_ant = N_ant;
+            fp.demap = ctx->demap; fp.vshift = N_id_cell % 6;
             fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
             int e = a;
             rc = fill_group(ctx, T, allocs, n_alloc, a, &e, fp);

@@ -53,6 +53,55 @@ __device__ __forceinline__ void zf_1port(float2 y, float2 h, float &xr, float &x
     xi = __fdiv_rn(__fsub_rn(__fmul_rn(y.y, h.x), __fmul_rn(y.x, h.y)), nrm);
 }
 
+// ---- soft path (BASELINE north star: "per-RE MMSE equalisation, soft QPSK/16QAM/64QAM demapping"; the reference equalises by zero forcing and
+// makes hard 16/64QAM decisions with a FIXME, liblte_phy.cc:7680-7690, :9576, :9607).  Off by default -- the reference-exact path is the parity
+// path -- and selected per context with lteb200_set_demapper(LTEB200_DEMAP_MAXLOG); it feeds the max-log-MAP decoder only.
+//
+// One antenna port: x_mmse = conj(h) y / (|h|^2 + s2) is biased by |h|^2 / (|h|^2 + s2); unbiased it is the zero-forcing symbol with noise
+// variance s2 / |h|^2, so the exact max-log LLR of a Gray-mapped bit is  g * (min_{s: b=1} |x - s|^2 - min_{s: b=0} |x - s|^2), g = |h|^2 / s2
+// (positive = bit 0, the reference's sign convention).  In units of the constellation's half spacing A (x = A u) the two minima are the
+// piecewise-linear functions below.  The int8 soft bit is round(2 * LLR) clamped to +-127.
+// s2 comes from the CRS: on symbol 0 the estimate at a pilot tone IS the least-squares estimate, so d_j = h_j - (h_{j-1} + h_{j+1}) / 2 over
+// neighbouring pilot tones has variance 1.5 s2 on a channel that is smooth over 12 subcarriers.
+__device__ __forceinline__ void maxlog_dim(float u, int Qm, float w[3])
+{
+    // u: one dimension (I or Q) in half-spacing units; w[0] = sign bit, w[1], w[2] = amplitude bits (as far as the constellation has them)
+    const float v = fabsf(u);
+    if (Qm == 2) { w[0] = __fmul_rn(4.0f, u); return; }
+    if (Qm == 4) {
+        w[0] = v <= 2.0f ? __fmul_rn(4.0f, u) : (u > 0.f ? __fsub_rn(__fmul_rn(8.0f, u), 8.0f) : __fadd_rn(__fmul_rn(8.0f, u), 8.0f));
+        w[1] = __fmul_rn(4.0f, __fsub_rn(2.0f, v));
+        return;
+    }
+    float a, c;        // sign bit: a u -+ c
+    if (v <= 2.0f) { a = 4.0f; c = 0.0f; } else if (v <= 4.0f) { a = 8.0f; c = 8.0f; } else if (v <= 6.0f) { a = 12.0f; c = 24.0f; } else { a = 16.0f; c = 48.0f; }
+    w[0] = u > 0.f ? __fsub_rn(__fmul_rn(a, u), c) : __fadd_rn(__fmul_rn(a, u), c);
+    w[1] = v <= 2.0f ? __fsub_rn(24.0f, __fmul_rn(8.0f, v)) : (v <= 6.0f ? __fsub_rn(16.0f, __fmul_rn(4.0f, v)) : __fsub_rn(40.0f, __fmul_rn(8.0f, v)));
+    w[2] = v <= 4.0f ? __fsub_rn(__fmul_rn(4.0f, v), 8.0f) : __fsub_rn(24.0f, __fmul_rn(4.0f, v));
+}
+// (xr, xi): unbiased equalised symbol; gain = post-equalisation SNR |h|^2 / s2; b[Qm] int8-range soft bits in the reference's bit order
+__device__ __forceinline__ void demap_maxlog(float xr, float xi, float gain, int mod, int b[6])
+{
+    const int Qm = mod == LTEB200_MOD_QPSK ? 2 : (mod == LTEB200_MOD_16QAM ? 4 : (mod == LTEB200_MOD_64QAM ? 6 : 1));
+    if (Qm == 1) {      // BPSK: points +-(1 + j)/sqrt(2): project on the diagonal
+        const float t = __fmul_rn(__fmul_rn(2.0f, gain), __fmul_rn(2.8284271247461903f, __fmul_rn(0.70710678118654752440f, __fadd_rn(xr, xi))));
+        b[0] = max(-127, min(127, __float2int_rn(t)));
+        return;
+    }
+    const float inv_a = Qm == 2 ? 1.4142135623730951f : (Qm == 4 ? 3.1622776601683795f : 6.4807406984078604f);     // 1 / A
+    const float a2 = Qm == 2 ? 0.5f : (Qm == 4 ? 0.1f : 0.023809523809523808f);                                      // A^2
+    const float k = __fmul_rn(__fmul_rn(2.0f, gain), a2);
+    float wi[3], wq[3];
+    maxlog_dim(__fmul_rn(xr, inv_a), Qm, wi);
+    maxlog_dim(__fmul_rn(xi, inv_a), Qm, wq);
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+        if (2 * t < Qm) {
+            b[2 * t] = max(-127, min(127, __float2int_rn(__fmul_rn(k, wi[t]))));
+            b[2 * t + 1] = max(-127, min(127, __float2int_rn(__fmul_rn(k, wq[t]))));
+        }
+}
+
 // ---- transmit-diversity combining shared by PDSCH, PBCH and PDCCH (pre_decoder_and_matched_filter_dl + layer_demapper_dl,
 // liblte_phy.cc:7691-7765, 7505-7512), in the reference's operation order (IEEE adds/multiplies, no contraction)
 __device__ __forceinline__ float td_sum4(float a, float b, float c, float d) { return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d); }
@@ -103,5 +152,7 @@ struct FusedParams {
     int32_t *crc_ok;
     int nsc, n_sf, n_alloc_total, tb_stride, n_al;
     int N_ant;                // 1: zero forcing; 2 / 4: transmit-diversity combining of groups of N_ant resource elements
+    int demap;                // LTEB200_DEMAP_*
+    int vshift;               // N_id_cell mod 6: offset of the port-0 pilot tones in symbol 0 (noise estimate of the soft path)
     FusedAlloc al[8];
 };

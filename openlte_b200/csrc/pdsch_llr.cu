@@ -31,6 +31,16 @@ __device__ __noinline__ void emit_soft(float xr, float xi, int mod, int Qm, cons
         if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
 }
 
+// soft path: equalised symbol + post-equalisation SNR -> max-log soft bits, descrambled
+__device__ __noinline__ void emit_maxlog(float xr, float xi, float gain, int mod, int Qm, const uint8_t *__restrict__ cs_r, int8_t *soft_r)
+{
+    int bb[6];
+    demap_maxlog(xr, xi, gain, mod, bb);
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
+}
+
 constexpr int LUT_MAX = 4096;     // table of q over -max..max (127 x 16 repeats each way); beyond it the division is done per value
 
 // first_kT: gather map in OUTPUT order: [x][pos] for the three streams (pos = (k mod 16) * NT + k / 16, -1 on the padding) followed by the 12
@@ -52,20 +62,64 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
     const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
     const int *ix = A.re_idx + cls * A.idx_stride;
     const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
+    const bool maxlog = fp.demap == LTEB200_DEMAP_MAXLOG;
+    __shared__ float s_s2;
+    if (maxlog) {
+        // noise variance from the pilot tones of symbol 0, port 0 (see pdsch_dev.cuh); one thread, fixed summation order (the CPU twin adds in
+        // the same order, oracle/port/softdemap.cc)
+        if (t == 0) {
+            const int n = fp.nsc / 6;
+            float acc = 0.f, pw = 0.f;
+            for (int j = 1; j + 1 < n; j++) {
+                const float2 c = ch[6 * j + fp.vshift], a = ch[6 * (j - 1) + fp.vshift], b = ch[6 * (j + 1) + fp.vshift];
+                const float dr = __fsub_rn(c.x, __fmul_rn(0.5f, __fadd_rn(a.x, b.x))), di = __fsub_rn(c.y, __fmul_rn(0.5f, __fadd_rn(a.y, b.y)));
+                acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di)));
+                pw = __fadd_rn(pw, __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
+            }
+            const float cnt = (float)(n - 2);
+            float s2 = __fdiv_rn(__fmul_rn(0.6666666865348816f, acc), cnt);
+            const float floor_ = __fmul_rn(__fdiv_rn(pw, cnt), 1e-6f);      // at most 60 dB
+            if (!(s2 > floor_)) s2 = floor_;
+            if (!(s2 > 0.f)) s2 = 1e-12f;
+            s_s2 = s2;
+        }
+        __syncthreads();
+    }
+    const float s2 = maxlog ? s_s2 : 1.0f;
     if (fp.N_ant != 1) {
         // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
         const size_t ps = (size_t)14 * fp.nsc;
+        auto pw2 = [](float2 h) { return __fadd_rn(__fmul_rn(h.x, h.x), __fmul_rn(h.y, h.y)); };
         for (int r = t * fp.N_ant; r < M; r += THREADS * fp.N_ant) {
             if (fp.N_ant == 2) {
                 float2 x0, x1;
-                sfbc2(gr[ix[r]], gr[ix[r + 1]], ch[ix[r]], ch[ps + ix[r]], x0, x1);
-                emit_soft(x0.x, x0.y, mod, Qm, cs + r * Qm, soft + r * Qm);
-                emit_soft(x1.x, x1.y, mod, Qm, cs + (r + 1) * Qm, soft + (r + 1) * Qm);
+                const float2 h0 = ch[ix[r]], h1 = ch[ps + ix[r]];
+                sfbc2(gr[ix[r]], gr[ix[r + 1]], h0, h1, x0, x1);
+                if (maxlog) {
+                    // the reference divides by sqrt(|h0|^4 + |h1|^4) (sic, liblte_phy.cc:7700); maximum-ratio combining divides by |h0|^2 + |h1|^2
+                    const float a0 = pw2(h0), a1 = pw2(h1), den = __fadd_rn(a0, a1);
+                    const float rs = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1))), den), g = __fdiv_rn(den, s2);
+                    emit_maxlog(__fmul_rn(x0.x, rs), __fmul_rn(x0.y, rs), g, mod, Qm, cs + r * Qm, soft + r * Qm);
+                    emit_maxlog(__fmul_rn(x1.x, rs), __fmul_rn(x1.y, rs), g, mod, Qm, cs + (r + 1) * Qm, soft + (r + 1) * Qm);
+                } else {
+                    emit_soft(x0.x, x0.y, mod, Qm, cs + r * Qm, soft + r * Qm);
+                    emit_soft(x1.x, x1.y, mod, Qm, cs + (r + 1) * Qm, soft + (r + 1) * Qm);
+                }
             } else {
                 const float2 y[4] = {gr[ix[r]], gr[ix[r + 1]], gr[ix[r + 2]], gr[ix[r + 3]]};
+                const float2 h0 = ch[ix[r]], h1 = ch[ps + ix[r + 2]], h2 = ch[2 * ps + ix[r]], h3 = ch[3 * ps + ix[r + 2]];
                 float2 x[4];
-                sfbc4(y, ch[ix[r]], ch[ps + ix[r + 2]], ch[2 * ps + ix[r]], ch[3 * ps + ix[r + 2]], x);
-                for (int q = 0; q < 4; q++) emit_soft(x[q].x, x[q].y, mod, Qm, cs + (r + q) * Qm, soft + (r + q) * Qm);
+                sfbc4(y, h0, h1, h2, h3, x);
+                if (maxlog) {
+                    const float a0 = pw2(h0), a1 = pw2(h1), a2 = pw2(h2), a3 = pw2(h3), d02 = __fadd_rn(a0, a2), d13 = __fadd_rn(a1, a3);
+                    const float r02 = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a2, a2))), d02), g02 = __fdiv_rn(d02, s2);
+                    const float r13 = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(a1, a1), __fmul_rn(a3, a3))), d13), g13 = __fdiv_rn(d13, s2);
+                    for (int q = 0; q < 4; q++) {
+                        const float rs = q < 2 ? r02 : r13, g = q < 2 ? g02 : g13;
+                        emit_maxlog(__fmul_rn(x[q].x, rs), __fmul_rn(x[q].y, rs), g, mod, Qm, cs + (r + q) * Qm, soft + (r + q) * Qm);
+                    }
+                } else
+                    for (int q = 0; q < 4; q++) emit_soft(x[q].x, x[q].y, mod, Qm, cs + (r + q) * Qm, soft + (r + q) * Qm);
             }
         }
     } else {
@@ -84,7 +138,11 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
                 if (r < M) {
                     float xr, xi;
                     zf_1port(yv[u], hv[u], xr, xi);
-                    emit_soft(xr, xi, mod, Qm, cs + r * Qm, soft + r * Qm);
+                    if (maxlog) {
+                        const float hh = __fadd_rn(__fmul_rn(hv[u].x, hv[u].x), __fmul_rn(hv[u].y, hv[u].y));
+                        emit_maxlog(xr, xi, __fdiv_rn(hh, s2), mod, Qm, cs + r * Qm, soft + r * Qm);
+                    } else
+                        emit_soft(xr, xi, mod, Qm, cs + r * Qm, soft + r * Qm);
                 }
             }
         }

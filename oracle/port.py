@@ -98,6 +98,26 @@ def demap(d_re, d_im, mod):
     out = np.zeros(6 * r.size, np.int8); n = lib().op_demap(_p(r), _p(i), int(r.size), mod, _p(out)); return out[:n]
 
 
+def noise_var_crs(h_re, h_im, vshift):
+    a = np.ascontiguousarray(h_re, np.float32); b = np.ascontiguousarray(h_im, np.float32)
+    lib().op_noise_var_crs.restype = C.c_float
+    return float(lib().op_noise_var_crs(_p(a), _p(b), int(a.size), int(vshift)))
+
+
+def soft_bits_1ant(y_re, y_im, h_re, h_im, mod, s2, cseq):
+    a = [np.ascontiguousarray(v, np.float32) for v in (y_re, y_im, h_re, h_im)]
+    qm = {0: 1, 1: 2, 2: 4, 3: 6}[mod]; M = a[0].size
+    cs = np.ascontiguousarray(cseq[:M * qm], np.uint8); out = np.zeros(M * qm, np.int8)
+    lib().op_soft_bits_1ant(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), M, mod, C.c_float(s2), _p(cs), _p(out)); return out
+
+
+def soft_bits_2ant(d_re, d_im, h0_re, h0_im, h1_re, h1_im, mod, s2, cseq):
+    a = [np.ascontiguousarray(v, np.float32) for v in (d_re, d_im, h0_re, h0_im, h1_re, h1_im)]
+    qm = {0: 1, 1: 2, 2: 4, 3: 6}[mod]; M = a[0].size
+    cs = np.ascontiguousarray(cseq[:M * qm], np.uint8); out = np.zeros(M * qm, np.int8)
+    lib().op_soft_bits_2ant(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), M, mod, C.c_float(s2), _p(cs), _p(out)); return out
+
+
 def pdsch_re_indices(N_rb_dl, N_id_cell, N_ant, subfr, cfi, prb, prb1=None):
     p0 = np.ascontiguousarray(prb, np.int32); p1 = p0 if prb1 is None else np.ascontiguousarray(prb1, np.int32)
     out = np.zeros(14 * 12 * p0.size, np.int32)

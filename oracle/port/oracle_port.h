@@ -49,6 +49,11 @@ void op_zf_1ant(const float *y_re, const float *y_im, const float *h_re, const f
 int  op_pre_decoder_dl(const float *y_re, const float *y_im, const float *h_re, const float *h_im, int h_len, int M, int N_ant,
                        float *d_re, float *d_im);
 int  op_demap(const float *d_re, const float *d_im, int M, int mod_type, int8_t *bits);
+/* ---- soft symbol level of the max-log-MAP path (no reference counterpart: twin of pdsch_llr.cu's LTEB200_DEMAP_MAXLOG branch, port/softdemap.cc) */
+float op_noise_var_crs(const float *h_re, const float *h_im, int nsc, int vshift);
+void  op_soft_bits_1ant(const float *y_re, const float *y_im, const float *h_re, const float *h_im, int M, int mod, float s2, const uint8_t *cseq, int8_t *soft);
+void  op_soft_bits_2ant(const float *d_re, const float *d_im, const float *h0_re, const float *h0_im, const float *h1_re, const float *h1_im, int M, int mod, float s2,
+                        const uint8_t *cseq, int8_t *soft);
 /* ---- RE extraction (a7): writes indices (symbol*1200+sc) of the PDSCH REs of one allocation */
 int  op_pdsch_re_indices(int N_rb_dl, int N_id_cell, int N_ant, int subfr_num, int N_pdcch_symbs, int N_prb,
                          const int *prb_slot0, const int *prb_slot1, int *idx);

@@ -1,0 +1,169 @@
+"""Symbol level of the max-log-MAP receive path (openlte_b200/csrc/pdsch_llr.cu) against the oracle, as quantised LLR images:
+
+  * reference demapper (default): RE walk, zero forcing, demapping, descrambling, rate unmatching and the decoder's input quantisation restated
+    with the oracle port (each piece pinned to the reference, tests/test_oracle_port.py): identical bytes for 16QAM / 64QAM, +-2 for QPSK
+    (atan2f differs from glibc's by ulps);
+  * north-star soft demapper (lteb200_set_demapper(LTEB200_DEMAP_MAXLOG): noise variance from the CRS, MMSE weighting, exact max-log LLRs) against
+    its float CPU twin oracle/port/softdemap.cc: identical bytes, one and two antenna ports;
+  * acceptance of the soft path: the rate-0.93 "north-star load" (12 x K = 6144 per 20 MHz subframe) decodes completely with
+    soft decisions where hard decisions leave CRC failures.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import dptr, stream_ptr
+
+pytestmark = pytest.mark.gpu
+
+QM = {1: 2, 2: 4, 3: 6}
+CONST = {1: np.array([1, -1]) / np.sqrt(2), 2: np.array([1, 3, -1, -3]) / np.sqrt(10), 3: np.array([3, 1, 5, 7, -3, -1, -5, -7]) / np.sqrt(42)}
+
+
+def make_grid(rng, n_sf, n_ant, mod, noise, nsc=1200):
+    """random smooth channel per port, grid = sum_p h_p * s + noise at every RE (not a real SFBC signal: the kernels are compared operation by
+    operation with the oracle, whatever the samples mean)"""
+    k = np.arange(nsc)
+    ce = np.zeros((n_sf, n_ant, 14, nsc), np.complex64)
+    for b in range(n_sf):
+        for p in range(n_ant):
+            a = (0.6 + rng.random()) * np.exp(2j * np.pi * rng.random())
+            ce[b, p] = (a * (1 + 0.2 * np.cos(2 * np.pi * (k / 400.0 + rng.random()))))[None, :] * np.exp(1j * 0.02 * np.arange(14))[:, None]
+    pts = CONST[mod]
+    s = (rng.choice(pts, (n_sf, 16, nsc)) + 1j * rng.choice(pts, (n_sf, 16, nsc))).astype(np.complex64)
+    grid = np.zeros((n_sf, 16, nsc), np.complex64)
+    grid[:, :14] = ce[:, 0] * s[:, :14]
+    grid += (noise * (rng.standard_normal(grid.shape) + 1j * rng.standard_normal(grid.shape))).astype(np.complex64)
+    ce += (0.3 * noise * (rng.standard_normal(ce.shape) + 1j * rng.standard_normal(ce.shape))).astype(np.complex64)
+    return grid, ce
+
+
+def f2(a):
+    return np.ascontiguousarray(np.stack([a.real, a.imag], -1).astype(np.float32))
+
+
+def oracle_image(port, grid_b, ce_b, n_ant, subfr, cell, cfi, al, K, NT, soft_mode):
+    """quantised image of one (subframe, allocation) from oracle pieces"""
+    mod, qm = al["mod"], QM[al["mod"]]
+    idx = port.pdsch_re_indices(100, cell, n_ant, subfr, cfi, al["prb"])
+    sym, sc = idx // 1200, idx % 1200
+    y = grid_b[sym, sc]
+    c = port.prs_c((al["rnti"] << 14) | (subfr << 9) | cell, idx.size * qm)
+    if n_ant == 1:
+        h = ce_b[0, sym, sc]
+        if soft_mode:
+            s2 = port.noise_var_crs(ce_b[0, 0].real, ce_b[0, 0].imag, cell % 6)
+            soft = port.soft_bits_1ant(y.real, y.imag, h.real, h.imag, mod, s2, c).astype(np.float32)
+        else:
+            xr, xi = port.zf_1ant(y.real, y.imag, h.real, h.imag)
+            soft = port.demap(xr, xi, mod).astype(np.float32) * (1.0 - 2.0 * c.astype(np.float32))
+    else:
+        h0, h1 = ce_b[0, sym, sc], ce_b[1, sym, sc]
+        hr = np.concatenate([h0.real, h1.real]).astype(np.float32); hi = np.concatenate([h0.imag, h1.imag]).astype(np.float32)
+        dr = np.zeros(idx.size, np.float32); di = np.zeros(idx.size, np.float32)
+        port.lib().op_pre_decoder_dl(port._p(np.ascontiguousarray(y.real, np.float32)), port._p(np.ascontiguousarray(y.imag, np.float32)), port._p(hr), port._p(hi),
+                                     int(idx.size), int(idx.size), 2, port._p(dr), port._p(di))
+        assert soft_mode
+        s2 = port.noise_var_crs(ce_b[0, 0].real, ce_b[0, 0].imag, cell % 6)
+        soft = port.soft_bits_2ant(dr, di, h0.real, h0.imag, h1.real, h1.imag, mod, s2, c).astype(np.float32)
+    d = port.rate_unmatch_turbo(soft, K + 4)
+    d[d == 10000.0] = 0.0
+    mx = np.float32(np.abs(d).max())
+    q = np.trunc((d * np.float32(127)) / mx).astype(np.int8) if mx > 0 else np.zeros(d.size, np.int8)
+    NP = 16 * NT
+    img = np.zeros(3 * NP + 16, np.int8)
+    kk = np.arange(K)
+    pos = (kk % 16) * NT + kk // 16
+    for x in range(3):
+        img[x * NP + pos] = q[3 * kk + x]
+    img[3 * NP:3 * NP + 12] = q[3 * K:3 * K + 12]
+    return img
+
+
+def gpu_images(ctx, lib, grid, ce, subfr, cell, cfi, allocs, n_ant, K, soft_mode):
+    import torch
+    from openlte_b200.lib import Alloc
+    n_sf = grid.shape[0]
+    stride = int(lib.q8_stride(K))
+    assert stride > 0
+    d_grid = torch.from_numpy(f2(grid)).cuda(); d_ce = torch.from_numpy(f2(ce)).cuda()
+    q8 = torch.zeros((len(allocs), n_sf, stride), dtype=torch.int8, device="cuda")
+    ca = (Alloc * len(allocs))(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    sn = np.asarray(subfr, np.int32)
+    ctx.check(lib.set_demapper(ctx.h, 1 if soft_mode else 0))
+    try:
+        ctx.check(lib.pdsch_llr_q8_batch(ctx.h, dptr(d_grid), dptr(d_ce), 100, cell, n_ant, sn.ctypes.data_as(C.c_void_p), n_sf, cfi, ca, len(allocs), dptr(q8),
+                                         stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        lib.set_demapper(ctx.h, 0)
+    return q8.cpu().numpy()
+
+
+@pytest.mark.parametrize("mod,soft_mode", [(3, False), (2, False), (1, False), (3, True), (2, True), (1, True)])
+def test_symbol_level_image_matches_oracle_1port(ctx, lib, port, mod, soft_mode):
+    rng = np.random.default_rng(40 + mod + 10 * soft_mode)
+    cell, cfi, n_sf = 77, 2, 3
+    subfr = [1, 5, 0]
+    # K = 2048 (tbs 2024) on 10 PRB and K = 2048 on 30 PRB (repeats: E > period)
+    allocs = [dict(mod=mod, prb=list(range(3, 13)), tbs=2024, rnti=0x1234), dict(mod=mod, prb=list(range(40, 70)), tbs=2024, rnti=0x77)]
+    grid, ce = make_grid(rng, n_sf, 1, mod, noise=0.05)
+    got = gpu_images(ctx, lib, grid, ce, subfr, cell, cfi, allocs, 1, 2048, soft_mode)
+    for a, al in enumerate(allocs):
+        for b in range(n_sf):
+            want = oracle_image(port, grid[b], ce[b], 1, subfr[b], cell, cfi, al, 2048, 128, soft_mode)
+            diff = np.abs(got[a, b].astype(int) - want.astype(int))
+            tol = 2 if (mod == 1 and not soft_mode) else 0          # QPSK reference demapper: atan2f ulps -> +-1 LSB per soft bit before the sums
+            assert diff.max() <= tol, f"mod={mod} soft={soft_mode} alloc {a} subframe {b}: {np.count_nonzero(diff > tol)} bytes differ (max {diff.max()})"
+
+
+def test_symbol_level_image_matches_oracle_2port_soft(ctx, lib, port):
+    rng = np.random.default_rng(5)
+    cell, cfi, n_sf = 301, 3, 2
+    subfr = [2, 7]
+    allocs = [dict(mod=2, prb=list(range(20, 36)), tbs=2024, rnti=0x99)]
+    grid, ce = make_grid(rng, n_sf, 2, 2, noise=0.05)
+    got = gpu_images(ctx, lib, grid, ce, subfr, cell, cfi, allocs, 2, 2048, True)
+    for b in range(n_sf):
+        want = oracle_image(port, grid[b], ce[b], 2, subfr[b], cell, cfi, allocs[0], 2048, 128, True)
+        assert np.array_equal(got[0, b], want), f"subframe {b}: {np.count_nonzero(got[0, b] != want)} bytes differ"
+
+
+def test_north_star_load_soft_decisions_beat_hard_decisions(ctx, lib):
+    """12 x (8 PRB, 64QAM, K = 6144): code rate 0.93, subframes 1-4 (in subframes 0 and 5 the centre allocations lose resource elements to
+    PBCH/PSS/SSS and their code rate exceeds 1: that, not the demapper, was the 0.967 CRC pass rate of the round-1 sweep).  Near the waterfall
+    (25 dB per resource element) the reference's hard 64QAM decisions lose about half of the blocks, max-log soft decisions with MMSE weighting an
+    eighth (profiles/r2_soft_vs_hard_bler.jsonl: about 1 dB); noise-free both decode everything."""
+    import torch
+    from openlte_b200 import synth
+    from openlte_b200.lib import Alloc
+    cell, cfi, n_sf = 42, 2, 4
+    allocs = [dict(mod=3, prb=list(range(8 * a, 8 * a + 8)), tbs=6120, rnti=0x300 + a) for a in range(12)]
+    ca = (Alloc * 12)(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fails = {}
+    for noise in (0.0, 1.6):
+        fails[noise] = {0: 0, 1: 0}
+        for first, seed in ((1, 3), (6, 4)):
+            tx = synth.make_subframes(n_sf, allocs, N_id_cell=cell, N_rb_dl=100, fs_idx=4, cfi=cfi, seed=seed, noise=noise, first_subfr=first)
+            stream = np.concatenate([tx["samples"].reshape(-1), synth.crs_only_tail(100, cell, (first + n_sf) % 10, 4)[:8192]])
+            iq = np.stack([stream.real, stream.imag], -1).astype(np.float32)
+            d_iq = torch.from_numpy(iq).cuda()
+            start = (np.arange(n_sf, dtype=np.int64) * 30720); sn = tx["subfr_nums"].astype(np.int32)
+            want = np.stack(tx["tb"], 1)
+            for demap in (0, 1):
+                tb = torch.zeros((n_sf, 12, 6120), dtype=torch.uint8, device="cuda"); ok = torch.zeros((n_sf, 12), dtype=torch.int32, device="cuda")
+                ctx.check(lib.set_demapper(ctx.h, demap))
+                try:
+                    ctx.check(lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), n_sf, cfi, ca, 12, 1, 8, dptr(tb), 6120,
+                                                   dptr(ok), stream_ptr()))
+                    torch.cuda.synchronize()
+                finally:
+                    lib.set_demapper(ctx.h, 0)
+                okh = ok.cpu().numpy() == 1
+                good = (tb.cpu().numpy() == want).all(axis=2)
+                assert np.array_equal(okh, good), "CRC verdict and bit equality disagree"
+                fails[noise][demap] += int((~good).sum())
+    assert fails[0.0] == {0: 0, 1: 0}
+    assert fails[1.6][0] >= 20 and 2 * fails[1.6][1] <= fails[1.6][0], f"failures of 96 blocks at 25 dB: hard {fails[1.6][0]}, soft {fails[1.6][1]}"
