@@ -108,6 +108,15 @@ __device__ __forceinline__ uint32_t bwd_step(uint32_t (&b)[8], const uint32_t (&
 
 // extrinsic of one lane: clamp(((L - Lsa) * 3) >> 2)
 __device__ __forceinline__ int ext_of(int d) { return clampi((d * 3) >> 2, -LE_LIM, LE_LIM); }
+// ((d * 3) >> 2) of both lanes: the high product word of (lane << 16) * (3 << 14) is (3 lane) >> 2 with an arithmetic shift.  Two IMAD.HI
+// (FMA pipe) instead of sign extension, multiply and shift per lane on the ALU pipe.
+__device__ __forceinline__ void ext_pair(uint32_t d2, int &eA, int &eB)
+{
+    eA = __mulhi((int)(d2 << 16), 3 << 14);
+    eB = __mulhi((int)(d2 & 0xffff0000u), 3 << 14);
+}
+constexpr uint32_t LE2 = (uint32_t)LE_LIM | ((uint32_t)LE_LIM << 16), NLE2 = (uint32_t)(-LE_LIM & 0xffff) | ((uint32_t)(-LE_LIM & 0xffff) << 16);
+constexpr uint32_t LA2 = (uint32_t)LA_LIM | ((uint32_t)LA_LIM << 16), NLA2 = (uint32_t)(-LA_LIM & 0xffff) | ((uint32_t)(-LA_LIM & 0xffff) << 16);
 
 // Shared-memory image of one code block (NT = row stride in windows of this size class, NT2 = NT/2 threads, NP = 16 NT positions;
 // position of trellis step k: (k mod 16) * NT + k / 16, so thread t's two windows are the adjacent columns 2t, 2t+1):
@@ -153,7 +162,7 @@ __device__ __forceinline__ void load_inputs(Smem<NT> &sm, const int t, const int
         for (int i = 0; i < 8; i++) {
             const int2 s = acc2[i * NT2];
             acc2[i * NT2] = make_int2(0, 0);
-            const uint32_t la = pk(clampi(s.x, -LA_LIM, LA_LIM), clampi(s.y, -LA_LIM, LA_LIM));
+            const uint32_t la = vmax(__vmins2(pk(s.x, s.y), LA2), NLA2);      // each sum is at most three extrinsics: fits a lane, clamped packed
             ls[i] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), la);
             lp[i] = s8x2_to_s16x2(Lp16[i * NT2]);
         }
@@ -212,13 +221,15 @@ __device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool a
             uint32_t d2;
             if ((i & 3) == 3) d2 = bwd_step<true>(b, al, ls, lp); else d2 = bwd_step<false>(b, al, ls, lp);
             d2 = vsub(d2, ls);
-            const int eA = ext_of(lo16(d2)), eB = ext_of(hi16(d2));
+            int eA, eB;
+            ext_pair(d2, eA, eB);
             if (SECOND) {
                 const uint32_t q2 = pi32[i * NT2];
-                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 & 0xffffu)), eA);
-                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 >> 16)), eB);
+                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 & 0xffffu)), clampi(eA, -LE_LIM, LE_LIM));
+                atomicAdd(reinterpret_cast<int *>(accb + 2 * (q2 >> 16)), clampi(eB, -LE_LIM, LE_LIM));
             } else {
-                S1w[i * NT2] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), pk(eA, eB));
+                // |(3 d) >> 2| < 2^15 (|d| < 2^15), so the pair packs before the clamp
+                S1w[i * NT2] = vadd(s8x2_to_s16x2(Ls16[i * NT2]), vmax(__vmins2(pk(eA, eB), LE2), NLE2));
             }
         };
         // ---- backward over steps 15..8
