@@ -259,6 +259,31 @@ int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_bits, int tb
                               int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
                               float *d_iq, void *stream);
 
+/* The same with everything LTE_fdd_dl_file_gen puts on the air besides the PDSCH (LTE_fdd_dl_fg_samp_buf.cc:321-575): synchronisation signals
+ * (liblte_phy_map_pss :5265, liblte_phy_map_sss :5520), PBCH (liblte_phy_bch_channel_encode :3863), PCFICH + PDCCH with one DCI 1A per allocation
+ * (liblte_phy_pdcch_channel_encode :4113), and transmit diversity over 2 / 4 antenna ports (layer_mapper_dl :7293, pre_coder_dl :7526, CRS of every
+ * port liblte_phy_map_crs :5144).  The grids are bit-identical to the reference transmitter's.
+ *   d_grid (optional): DEVICE [n_sf][N_ant][14][12 N_rb_dl] float2;  d_iq (optional): DEVICE [n_sf][1920 << fs_idx] float2, the ports' signals
+ *   summed with the flat per-port channel gains of `ctl`.
+ * PCFICH/PDCCH: one antenna port only (like the receive side); at most four allocations (common search space, aggregation level 4), each QPSK with
+ * contiguous PRBs, an SI/P/RA-RNTI and tbs = lteb200_dci_1a_tbs(mcs) -- what the reference's dci_1a_unpack understands. */
+typedef struct {
+    int32_t N_id_cell;
+    int32_t N_ant;                       /* 1, 2 or 4 */
+    float   ant_gain_re[4], ant_gain_im[4];
+    int32_t sync;                        /* 1: PSS + SSS in subframes 0 and 5 */
+    int32_t pbch;                        /* 1: PBCH in every subframe 0 */
+    int32_t sfn_first;                   /* system frame number of the frame the first subframe of the batch belongs to */
+    const uint8_t *mib_bits;             /* HOST [n_frames][24], one bit per byte; frame f of the batch begins at the f-th subframe number 0 (f = 0: the first, possibly partial one) */
+    int32_t pdcch;                       /* 1: PCFICH + PDCCH */
+    float   phich_res;                   /* Ng: 1/6, 1/2, 1 or 2 (PHICH groups are reserved, nothing is sent on them) */
+    int32_t mcs[8];                      /* MCS field of each allocation's DCI */
+} lteb200_tx_control;
+int lteb200_dci_1a_tbs(int mcs);         /* 36.213 table 7.1.7.2.1-1, column N_PRB = 3 (what DCI 1A with an SI/P/RA-RNTI implies), -1 if mcs > 26 */
+int lteb200_dl_transmit_frames_batch(lteb200_ctx *ctx, const uint8_t *d_tb_bits, int tb_stride, const lteb200_alloc *allocs, int n_alloc, int fs_idx,
+                                     int N_rb_dl, const lteb200_tx_control *ctl, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
+                                     float *d_iq, void *stream);
+
 /* -------------------------------------------------------------------------------------------- front end */
 /* LTE_fdd_dl_fs_samp_buf::freq_shift (LTE_fdd_dl_file_scan/src/LTE_fdd_dl_fs_samp_buf.cc:696-713) and the int8 -> float
  * conversion of copy_input_to_samp_buf (:657-694).  d_iq_in: DEVICE samples in iq_fmt; d_iq_out: DEVICE float2 [n_samps].

@@ -724,3 +724,268 @@ extern "C" int lteb200_pdcch_channel_decode(lteb200_ctx *ctx, const float *rx_sy
     *N_alloc = (uint32_t)n;
     return rc;
 }
+
+// =====================================================================================================================================
+// Transmit side of the control region and of the synchronisation / broadcast signals, for test-signal generation on
+// the device.  Twins of liblte_phy_map_pss :5265, liblte_phy_map_sss :5520, liblte_phy_bch_channel_encode :3863 (+ bch_channel_encode
+// :12510), pcfich_channel_map :7805 (+ cfi_channel_encode :13616), liblte_phy_pdcch_channel_encode :4113 (+ dci_1a_pack :13153,
+// dci_channel_encode :12882, conv_encode :9997, rate_match_conv :11499).  The bit-level encoding of the few distinct messages (one MIB per
+// 40 ms, one DCI per allocation) is host work; everything per subframe and per resource element -- scrambling with the subframe's Gold
+// sequence, QPSK mapping, CCE placement, REG interleaving / cyclic shift / resource mapping (through the receiver's own CCE map, inverted)
+// -- is one kernel with one CTA per subframe.  One antenna port for PCFICH/PDCCH (the reference is undefined beyond, see the receive side).
+namespace {
+
+unsigned crc16_host(const uint8_t *b, int n)        // calc_crc with CRC16 = 0x11021, liblte_phy.cc:9713-9743
+{
+    unsigned rem = 0;
+    for (int i = 0; i < n + 16; i++) {
+        rem = (rem << 1) | (i < n ? (b[i] & 1u) : 0u);
+        if (rem & 0x10000u) rem ^= 0x11021u;
+    }
+    return rem & 0xffffu;
+}
+// tail-biting convolutional code, constraint length 7, g = {0133, 0171, 0165} (conv_encode with tail_bit = true, liblte_phy.cc:9997-10057)
+void conv_encode_tb(const uint8_t *c, int n, uint8_t *d /*[3 n], d[3 i + j]*/)
+{
+    const unsigned g[3] = {0133, 0171, 0165};
+    uint8_t s[7];
+    for (int i = 0; i < 7; i++) s[i] = c[n - i - 1];
+    for (int i = 0; i < n; i++) {
+        for (int j = 6; j > 0; j--) s[j] = s[j - 1];
+        s[0] = c[i];
+        for (int j = 0; j < 3; j++) {
+            unsigned acc = 0;
+            for (int k = 0; k < 7; k++) acc += s[k] * ((g[j] >> (6 - k)) & 1u);
+            d[3 * i + j] = (uint8_t)(acc & 1u);
+        }
+    }
+}
+// rate_match_conv: the circular buffer read in the order of the sub-block interleaver, NULLs skipped
+void rate_match_cc(const uint8_t *d, int n_c, int n_e, uint8_t *e)
+{
+    const std::vector<int16_t> order = cc_order_host(n_c);
+    for (int k = 0; k < n_e; k++) e[k] = d[order[(size_t)k % order.size()]];
+}
+
+struct CtrlTxParams {
+    const int32_t *cce_re;      // [576] for this N_symbs
+    const int32_t *pcfich_re;   // [16]
+    const uint8_t *c_pdcch;     // [10][1152]
+    const uint8_t *c_pcfich;    // [10][32]
+    const uint8_t *dci_e;       // [n_dci][288] encoded + rate matched DCIs
+    const uint8_t *bch_e;       // [n_bch_rows][480] encoded, rate matched and scrambled PBCH bits of one radio frame
+    const int32_t *bch_row;     // [n_sf] row of bch_e for subframes that carry the PBCH, else -1
+    const float2 *sync;         // [3][62] PSS, SSS of subframe 0, SSS of subframe 5
+    const int *subfr_num;
+    float2 *grid;               // port-0 plane of subframe sf at grid + sf * sf_stride
+    size_t sf_stride, port_stride;
+    int nsc, n_dci, cfi, N_id_cell, N_ant, do_sync, do_pdcch;
+};
+
+__device__ __forceinline__ float2 qpsk(int b0, int b1)
+{
+    const float r = (float)(1.0 / sqrt(2.0));        // modulation_mapper, liblte_phy.cc:8740-8747
+    return make_float2(__fmul_rn(1.f - 2.f * (float)b0, r), __fmul_rn(1.f - 2.f * (float)b1, r));
+}
+
+__global__ void __launch_bounds__(128)
+ctrl_tx_kernel(const __grid_constant__ CtrlTxParams P)
+{
+    const int sf = blockIdx.x, t = threadIdx.x;
+    const int sn = P.subfr_num[sf];
+    float2 *g = P.grid + (size_t)sf * P.sf_stride;
+    if (P.do_pdcch) {
+        // PCFICH: 32-bit CFI code word, scrambled, 16 QPSK symbols on four REGs of symbol 0
+        if (t < 16) {
+            const unsigned w = kCfiWords[P.cfi - 1];
+            const uint8_t *c = P.c_pcfich + sn * 32;
+            g[P.pcfich_re[t]] = qpsk(((w >> (2 * t)) & 1u) ^ c[2 * t], ((w >> (2 * t + 1)) & 1u) ^ c[2 * t + 1]);
+        }
+        // PDCCH: DCI a occupies CCEs 4a .. 4a+3 of the common search space; 144 QPSK symbols each; the REs of every other CCE stay zero
+        const uint8_t *c = P.c_pdcch + sn * 1152;
+        for (int m = t; m < 144 * P.n_dci; m += blockDim.x) {
+            const int a = m / 144, j = m - a * 144;
+            const uint8_t *e = P.dci_e + a * 288;
+            const int re = P.cce_re[a * 144 + j];
+            if (re >= 0) g[re] = qpsk(e[2 * j] ^ c[a * 288 + 2 * j], e[2 * j + 1] ^ c[a * 288 + 2 * j + 1]);
+        }
+    }
+    if (P.do_sync && (sn == 0 || sn == 5)) {
+        // PSS in symbol 6, SSS in symbol 5, 62 subcarriers around DC, on every port (liblte_phy.cc:5265, :5520)
+        if (t < 62) {
+            const int k = t - 31 + P.nsc / 2;
+            for (int p = 0; p < P.N_ant; p++) {
+                g[p * P.port_stride + 6 * P.nsc + k] = P.sync[t];
+                g[p * P.port_stride + 5 * P.nsc + k] = P.sync[(sn == 0 ? 62 : 124) + t];
+            }
+        }
+    }
+    const int row = P.bch_row[sf];
+    if (row >= 0) {
+        // PBCH: 240 QPSK symbols (transmit diversity for 2 / 4 ports), symbols 7-10 of subframe 0, CRS positions of four ports left out in
+        // symbols 7 and 8 (liblte_phy.cc:3934-3953).  The reference advances its symbol index over the ports without resetting it (idx, :3936):
+        // port p's symbols 7/8 carry y_p[48 p + ...]; restated as is.
+        const uint8_t *e = P.bch_e + (size_t)row * 480;
+        const float r2 = (float)(1.0 / sqrt(2.0));
+        auto y = [&](int p, int i) -> float2 {                  // pre_coder_dl output of port p, symbol i (liblte_phy.cc:7526-7640)
+            if (P.N_ant == 1) return qpsk(e[2 * i], e[2 * i + 1]);
+            if (P.N_ant == 2) {
+                const int i0 = i & ~1;
+                const float2 d0 = qpsk(e[2 * i0], e[2 * i0 + 1]), d1 = qpsk(e[2 * i0 + 2], e[2 * i0 + 3]);
+                if (p == 0) return (i & 1) ? make_float2(__fmul_rn(r2, d1.x), __fmul_rn(r2, d1.y)) : make_float2(__fmul_rn(r2, d0.x), __fmul_rn(r2, d0.y));
+                return (i & 1) ? make_float2(__fmul_rn(r2, d0.x), __fmul_rn(-r2, d0.y)) : make_float2(__fmul_rn(-r2, d1.x), __fmul_rn(r2, d1.y));
+            }
+            const int i0 = i & ~3, q = i & 3;
+            const float2 d0 = qpsk(e[2 * i0], e[2 * i0 + 1]), d1 = qpsk(e[2 * i0 + 2], e[2 * i0 + 3]);
+            const float2 d2 = qpsk(e[2 * i0 + 4], e[2 * i0 + 5]), d3 = qpsk(e[2 * i0 + 6], e[2 * i0 + 7]);
+            const float2 zero = make_float2(0.f, 0.f);
+            if (p == 0) return q == 0 ? make_float2(__fmul_rn(r2, d0.x), __fmul_rn(r2, d0.y)) : (q == 1 ? make_float2(__fmul_rn(r2, d1.x), __fmul_rn(r2, d1.y)) : zero);
+            if (p == 1) return q == 2 ? make_float2(__fmul_rn(r2, d2.x), __fmul_rn(r2, d2.y)) : (q == 3 ? make_float2(__fmul_rn(r2, d3.x), __fmul_rn(r2, d3.y)) : zero);
+            if (p == 2) return q == 0 ? make_float2(__fmul_rn(-r2, d1.x), __fmul_rn(r2, d1.y)) : (q == 1 ? make_float2(__fmul_rn(r2, d0.x), __fmul_rn(-r2, d0.y)) : zero);
+            return q == 2 ? make_float2(__fmul_rn(-r2, d3.x), __fmul_rn(r2, d3.y)) : (q == 3 ? make_float2(__fmul_rn(r2, d2.x), __fmul_rn(-r2, d2.y)) : zero);
+        };
+        if (t < 72) {
+            const int k = P.nsc / 2 - 36 + t;
+            // rank of this subcarrier among the non-CRS ones of symbols 7 and 8
+            int idx = 0;
+            for (int i = 0; i < t; i++) idx += (P.N_id_cell % 3) != (i % 3);
+            for (int p = 0; p < P.N_ant; p++) {
+                float2 *gp = g + p * P.port_stride;
+                if ((P.N_id_cell % 3) != (t % 3)) {
+                    gp[7 * P.nsc + k] = y(p, 48 * p + idx);
+                    gp[8 * P.nsc + k] = y(p, 48 * p + idx + 48);
+                }
+                gp[9 * P.nsc + k] = y(p, t + 96);
+                gp[10 * P.nsc + k] = y(p, t + 168);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// DCI format 1A of one allocation (dci_1a_pack, liblte_phy.cc:13153-13250: localized VRBs, HARQ process 0) and its channel coding to 288 bits
+// (dci_channel_encode :12882, aggregation level 4).  Returns the transport block size the receiver will derive (36.213 7.1.7), or -1.
+static int dci_1a_encode_host(const lteb200_alloc &al, int mcs, int N_rb_dl, uint8_t *e288)
+{
+    if (al.N_prb < 1 || al.N_prb > N_rb_dl || mcs < 0 || mcs > 26) return -1;
+    for (int j = 1; j < al.N_prb; j++) if (al.prb[0][j] != al.prb[0][0] + j) return -1;     // resource allocation type 2: contiguous
+    const bool common = al.rnti == 0xFFFF || al.rnti == 0xFFFE || (al.rnti >= 0x0001 && al.rnti <= 0x003C);
+    uint8_t dci[64];
+    int n = 0;
+    auto put = [&](unsigned v, int bits) { for (int i = bits - 1; i >= 0; i--) dci[n++] = (uint8_t)((v >> i) & 1u); };
+    put(1, 1);                                           // format 0/1A flag: 1A
+    put(0, 1);                                           // localized VRBs
+    const int riv_len = (int)ceilf(logf((float)(N_rb_dl * (N_rb_dl + 1) / 2)) / logf(2.0f));
+    unsigned riv;
+    if ((al.N_prb - 1) <= N_rb_dl / 2) riv = (unsigned)(N_rb_dl * (al.N_prb - 1) + al.prb[0][0]);
+    else riv = (unsigned)(N_rb_dl * (N_rb_dl - al.N_prb + 1) + (N_rb_dl - 1 - al.prb[0][0]));
+    put(riv, riv_len);
+    put((unsigned)mcs, 5);
+    put(0, 3);                                           // HARQ process
+    put(0, 1);                                           // new data indicator
+    put((unsigned)al.rv_idx, 2);
+    put(common ? 1u : 0u, 2);                            // TPC; for SI/P/RA-RNTI its LSB selects N_PRB^1A = 3
+    if (n == 12 || n == 14 || n == 16 || n == 20 || n == 24 || n == 26 || n == 32 || n == 40 || n == 44 || n == 56) put(0, 1);
+    // CRC16 masked with the RNTI
+    const unsigned crc = crc16_host(dci, n) ^ (unsigned)(al.rnti & 0xffff);
+    uint8_t c[80], d[240];
+    memcpy(c, dci, n);
+    for (int i = 0; i < 16; i++) c[n + i] = (uint8_t)((crc >> (15 - i)) & 1u);
+    conv_encode_tb(c, n + 16, d);
+    rate_match_cc(d, n + 16, 288, e288);
+    return common ? kTbsNprb3[mcs] : -1;                 // the reference's receiver handles SI/P/RA-RNTI only (dci_1a_unpack, :13273)
+}
+extern "C" int lteb200_dci_1a_tbs(int mcs) { return (mcs >= 0 && mcs <= 26) ? kTbsNprb3[mcs] : -1; }
+
+// 24 MIB bits -> 1920 coded, rate matched and scrambled bits (4 x 480: one row per radio frame of the 40 ms period)
+static void bch_encode_host(const uint8_t *mib24, int N_ant, int N_id_cell, uint8_t *out1920)
+{
+    uint8_t c[40], d[120];
+    const unsigned mask = N_ant == 1 ? 0x0000u : (N_ant == 2 ? 0xFFFFu : 0x5555u);          // bch_channel_encode, liblte_phy.cc:12521-12546
+    const unsigned crc = crc16_host(mib24, 24) ^ mask;
+    memcpy(c, mib24, 24);
+    for (int i = 0; i < 16; i++) c[24 + i] = (uint8_t)((crc >> (15 - i)) & 1u);
+    conv_encode_tb(c, 40, d);
+    rate_match_cc(d, 40, 1920, out1920);
+    std::vector<uint8_t> s(1920);
+    prs_c_host((uint32_t)N_id_cell, 1920, s.data());
+    for (int i = 0; i < 1920; i++) out1920[i] ^= s[i];
+}
+
+void gen_pss(int N_id_2, float2 *out);                                   // sync.cu (generate_pss / generate_sss twins)
+void gen_sss(int N_id_1, int N_id_2, float2 *s0, float2 *s5);
+
+// Control region, synchronisation signals and PBCH into the grids of n_sf subframes.  grid: port-0 plane of subframe sf at grid + sf * sf_stride
+// floats2, port p at + p * port_stride.  Called by lteb200_dl_transmit_frames_batch (tx.cu).
+int control_tx_launch(lteb200_ctx *ctx, float2 *grid, size_t sf_stride, size_t port_stride, const int *d_sn, const int *h_sn, int n_sf, int N_rb_dl,
+                      int cfi, const lteb200_tx_control *ctl, const lteb200_alloc *allocs, int n_alloc, cudaStream_t stream)
+{
+    const int N_id_cell = ctl->N_id_cell, N_ant = ctl->N_ant;
+    if (ctl->pdcch && N_ant != 1) { lteb200_set_error(ctx, "dl_transmit: PCFICH/PDCCH for one antenna port only (as the receive side)"); return LTEB200_ERR_UNSUPPORTED; }
+    if (ctl->pdcch && (n_alloc > 4 || cfi < 1 || cfi > 3)) { lteb200_set_error(ctx, "dl_transmit: at most 4 DCIs (common search space, aggregation level 4), CFI 1..3"); return LTEB200_ERR_ARGS; }
+    std::lock_guard<std::mutex> lk(g_ctl_mu);
+    CtrlTxParams P;
+    memset(&P, 0, sizeof(P));
+    P.grid = grid; P.sf_stride = sf_stride; P.port_stride = port_stride; P.nsc = 12 * N_rb_dl; P.cfi = cfi; P.N_id_cell = N_id_cell; P.N_ant = N_ant;
+    P.subfr_num = d_sn; P.do_sync = ctl->sync; P.do_pdcch = ctl->pdcch;
+    StreamScope scope;
+    std::vector<uint8_t> host_blob;
+    // ---- DCIs
+    std::vector<uint8_t> dci_e((size_t)288 * (n_alloc > 0 ? n_alloc : 1), 0);
+    if (ctl->pdcch) {
+        PdcchTables T;
+        int rc = get_pdcch_tables(ctx, N_rb_dl, N_id_cell, 1, ctl->phich_res, &T);
+        if (rc) return rc;
+        const int n_symbs = cfi + (N_rb_dl <= 10 ? 1 : 0);
+        P.cce_re = T.cce_re + (n_symbs - 1) * 576; P.pcfich_re = T.pcfich_re; P.c_pdcch = T.c_pdcch; P.c_pcfich = T.c_pcfich;
+        for (int a = 0; a < n_alloc; a++) {
+            const int tbs = dci_1a_encode_host(allocs[a], ctl->mcs[a], N_rb_dl, dci_e.data() + 288 * a);
+            if (tbs < 0 || tbs != allocs[a].tbs || allocs[a].mod_type != LTEB200_MOD_QPSK) {
+                lteb200_set_error(ctx, "dl_transmit: allocation %d cannot be announced by a DCI 1A the reference's receiver understands (SI/P/RA-RNTI, contiguous PRBs, QPSK, "
+                                       "tbs = table 7.1.7.2.1-1[mcs][N_PRB = 3] = %d)", a, tbs);
+                return LTEB200_ERR_ARGS;
+            }
+        }
+        P.n_dci = n_alloc;
+    }
+    // ---- PBCH rows: frame f of the batch starts at the f-th subframe number 0 (f = 0: the possibly partial first frame)
+    std::vector<int32_t> bch_row(n_sf, -1);
+    std::vector<uint8_t> bch_e;
+    if (ctl->pbch) {
+        if (!ctl->mib_bits) { lteb200_set_error(ctx, "dl_transmit: pbch without mib_bits"); return LTEB200_ERR_ARGS; }
+        int frame = 0, group_mib = 0;
+        bool have = false;
+        uint8_t cur[1920];
+        for (int i = 0; i < n_sf; i++) {
+            if (i > 0 && h_sn[i] == 0 && h_sn[i - 1] != 0) frame++;
+            if (h_sn[i] != 0) continue;
+            const int sfn = ctl->sfn_first + frame;
+            // the reference encodes when its buffer is empty (first call, or after the frame with sfn mod 4 == 3) from the MIB it is given then
+            if (!have) { group_mib = frame; bch_encode_host(ctl->mib_bits + 24 * (size_t)group_mib, N_ant, N_id_cell, cur); have = true; }
+            bch_row[i] = (int32_t)(bch_e.size() / 480);
+            bch_e.insert(bch_e.end(), cur + (sfn % 4) * 480, cur + (sfn % 4) * 480 + 480);
+            if (sfn % 4 == 3) have = false;
+        }
+    }
+    // ---- sync sequences
+    std::vector<float2> sync(3 * 62);
+    if (ctl->sync) { gen_pss(N_id_cell % 3, sync.data()); gen_sss(N_id_cell / 3, N_id_cell % 3, sync.data() + 62, sync.data() + 124); }
+    uint8_t *d_dci = nullptr, *d_bch = nullptr;
+    int32_t *d_row = nullptr;
+    float2 *d_sync = nullptr;
+    LTE_CUDA_OK(ctx, scope.alloc(&d_dci, dci_e.size(), stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_bch, bch_e.size() ? bch_e.size() : 16, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_row, sizeof(int32_t) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_sync, sizeof(float2) * sync.size(), stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_dci, dci_e.data(), dci_e.size(), cudaMemcpyHostToDevice, stream));
+    if (bch_e.size()) LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_bch, bch_e.data(), bch_e.size(), cudaMemcpyHostToDevice, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_row, bch_row.data(), sizeof(int32_t) * n_sf, cudaMemcpyHostToDevice, stream));
+    LTE_CUDA_OK(ctx, cudaMemcpyAsync(d_sync, sync.data(), sizeof(float2) * sync.size(), cudaMemcpyHostToDevice, stream));
+    P.dci_e = d_dci; P.bch_e = d_bch; P.bch_row = d_row; P.sync = d_sync;
+    ctrl_tx_kernel<<<n_sf, 128, 0, stream>>>(P);
+    ctx->launches += 1;
+    LTE_CUDA_OK(ctx, cudaGetLastError());
+    LTE_CUDA_OK(ctx, cudaStreamSynchronize(stream));      // the pageable host vectors above must outlive their copies
+    return LTEB200_OK;
+}

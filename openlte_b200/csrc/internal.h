@@ -38,3 +38,6 @@ int pdsch_llr_q8_launch(lteb200_ctx *ctx, const FusedParams &fp, int K, int E_ma
 int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d_ce, int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num,
                            const int *d_subfr_dev, int n_sf, int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
                            uint8_t *d_tb_bits, int tb_stride, int32_t *d_crc_ok, cudaStream_t stream);
+// control region, synchronisation signals and PBCH of the transmit side (control.cu)
+int control_tx_launch(lteb200_ctx *ctx, float2 *grid, size_t sf_stride, size_t port_stride, const int *d_sn, const int *h_sn, int n_sf, int N_rb_dl,
+                      int cfi, const lteb200_tx_control *ctl, const lteb200_alloc *allocs, int n_alloc, cudaStream_t stream);

@@ -103,6 +103,9 @@ struct DevBuf {
 static inline size_t at_least_one(size_t b) { return b ? b : 1; }
 #define ALLOC(ctx, buf, bytes) LTE_CUDA_OK(ctx, cudaMalloc(&(buf).p, at_least_one((size_t)(bytes))))
 
+}  // namespace
+
+// (external linkage: the transmit side in control.cu maps the same sequences)
 void gen_pss(int N_id_2, float2 *out)
 {
     // generate_pss, liblte_phy.cc:8342-8368 (same expression, host libm)
@@ -131,6 +134,8 @@ void gen_sss(int N_id_1, int N_id_2, float2 *s0, float2 *s5)
         s5[2 * i] = make_float2((float)(a1 * c0), 0.f); s5[2 * i + 1] = make_float2((float)(a0 * c1 * z1), 0.f);
     }
 }
+
+namespace {
 
 // uploads split I/Q [lo, hi) (plus `pad` zero samples behind it), optionally also as an interleaved float2 stream
 int upload_iq(lteb200_ctx *ctx, const float *is, const float *qs, long long lo, long long hi, DevBuf &di, DevBuf &dq, DevBuf *diq, long long pad = 0)

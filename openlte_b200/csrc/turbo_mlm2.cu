@@ -106,8 +106,6 @@ __device__ __forceinline__ uint32_t bwd_step(uint32_t (&b)[8], const uint32_t (&
     return vsub(L0, L1);
 }
 
-// extrinsic of one lane: clamp(((L - Lsa) * 3) >> 2)
-__device__ __forceinline__ int ext_of(int d) { return clampi((d * 3) >> 2, -LE_LIM, LE_LIM); }
 // ((d * 3) >> 2) of both lanes: the high product word of (lane << 16) * (3 << 14) is (3 lane) >> 2 with an arithmetic shift.  Two IMAD.HI
 // (FMA pipe) instead of sign extension, multiply and shift per lane on the ALU pipe.
 __device__ __forceinline__ void ext_pair(uint32_t d2, int &eA, int &eB)

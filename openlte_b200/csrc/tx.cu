@@ -26,7 +26,8 @@ struct TxParams {
     const uint8_t *tb;        // [n_sf][n_alloc_total][tb_stride]
     const uint16_t *pi;       // [K]
     const uint32_t *crc_tab;  // x^j mod g
-    float2 *grid;             // [n_sf][14][nsc]
+    float2 *grid;             // [n_sf][N_ant][14][nsc]
+    int N_ant;
 };
 
 // rank in the circular buffer -> code-word index, from the receiver's first_k (rank of every code-word bit, -1 if never sent)
@@ -116,54 +117,92 @@ dlsch_encode_kernel(const __grid_constant__ TxParams P)
     const int M = A.M[cls];
     const int *ix = A.re_idx + cls * A.idx_stride;
     const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
-    float2 *g = P.grid + (size_t)sf * 14 * P.nsc;
-    for (int r = tid; r < M; r += blockDim.x) {
+    const size_t ps = (size_t)14 * P.nsc;
+    float2 *g = P.grid + (size_t)sf * P.N_ant * ps;
+    auto symbol = [&](int r) -> float2 {
         uint8_t b[6];
         for (int t = 0; t < A.Qm; t++) {
             const int k = r * A.Qm + t;
             b[t] = d[A.order[k % A.period]] ^ cs[k];
         }
-        g[ix[r]] = map_symbol(b, A.mod);
+        return map_symbol(b, A.mod);
+    };
+    if (P.N_ant == 1) {
+        for (int r = tid; r < M; r += blockDim.x) g[ix[r]] = symbol(r);
+        return;
+    }
+    // transmit diversity (layer_mapper_dl + pre_coder_dl, liblte_phy.cc:7293-7345, :7526-7640): groups of N_ant symbols, M a multiple of N_ant
+    const float r2 = (float)(1 / sqrt(2.0));
+    auto sc = [&](float2 v, float sr, float si) { return make_float2(__fmul_rn(sr, v.x), __fmul_rn(si, v.y)); };
+    for (int r = tid * P.N_ant; r < M; r += blockDim.x * P.N_ant) {
+        if (P.N_ant == 2) {
+            const float2 d0 = symbol(r), d1 = symbol(r + 1);
+            g[ix[r]] = sc(d0, r2, r2);          g[ix[r + 1]] = sc(d1, r2, r2);
+            g[ps + ix[r]] = sc(d1, -r2, r2);    g[ps + ix[r + 1]] = sc(d0, r2, -r2);
+        } else {
+            const float2 d0 = symbol(r), d1 = symbol(r + 1), d2 = symbol(r + 2), d3 = symbol(r + 3), z = make_float2(0.f, 0.f);
+            g[ix[r]] = sc(d0, r2, r2);              g[ix[r + 1]] = sc(d1, r2, r2);              g[ix[r + 2]] = z;                           g[ix[r + 3]] = z;
+            g[ps + ix[r]] = z;                      g[ps + ix[r + 1]] = z;                      g[ps + ix[r + 2]] = sc(d2, r2, r2);         g[ps + ix[r + 3]] = sc(d3, r2, r2);
+            g[2 * ps + ix[r]] = sc(d1, -r2, r2);    g[2 * ps + ix[r + 1]] = sc(d0, r2, -r2);    g[2 * ps + ix[r + 2]] = z;                  g[2 * ps + ix[r + 3]] = z;
+            g[3 * ps + ix[r]] = z;                  g[3 * ps + ix[r + 1]] = z;                  g[3 * ps + ix[r + 2]] = sc(d3, -r2, r2);    g[3 * ps + ix[r + 3]] = sc(d2, r2, -r2);
+        }
     }
 }
 
-// CRS of antenna port 0 into an otherwise zeroed grid: symbols 0, 4, 7, 11 (liblte_phy_map_crs, liblte_phy.cc:5144-5240)
+// CRS of every antenna port into an otherwise zeroed grid (liblte_phy_map_crs, liblte_phy.cc:5144-5240): ports 0 / 1 in symbols 0, 4, 7, 11
+// with frequency offsets (0,3,0,3) / (3,0,3,0), ports 2 / 3 in symbols 1, 8 with offsets (0,3) / (3,6); sequence of (slot, l) from the cell's table.
 __global__ void crs_map_kernel(const float2 *__restrict__ crs /*[20][3][220]*/, const int *__restrict__ subfr_num, int N_rb_dl, int N_id_cell, int nsc,
-                               float2 *__restrict__ grid)
+                               int N_ant, float2 *__restrict__ grid /*[n_sf][N_ant][14][nsc]*/)
 {
-    const int sf = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 4 * 2 * N_rb_dl) return;
+    const int sf = blockIdx.y, p = blockIdx.z, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_sym = p < 2 ? 4 : 2;
+    if (t >= n_sym * 2 * N_rb_dl) return;
     const int which = t / (2 * N_rb_dl), j = t - which * 2 * N_rb_dl;
-    const int sym = which == 0 ? 0 : (which == 1 ? 4 : (which == 2 ? 7 : 11));
-    const int slot = which >> 1, li = (which & 1) ? 2 : 0, v = (which & 1) ? 3 : 0;     // l = 0 -> table row 0, l = 4 -> row 2
+    int sym, v;
+    if (p < 2) { sym = which == 0 ? 0 : (which == 1 ? 4 : (which == 2 ? 7 : 11)); v = ((which & 1) ^ p) ? 3 : 0; }
+    else { sym = which == 0 ? 1 : 8; v = (which == 0 ? 0 : 3) + (p == 3 ? 3 : 0); }
+    const int slot = sym / 7, l = sym % 7, li = l == 0 ? 0 : (l == 1 ? 1 : 2);
     const int ns = 2 * subfr_num[sf] + slot;
-    grid[((size_t)sf * 14 + sym) * nsc + 6 * j + (v + N_id_cell % 6) % 6] = crs[((size_t)ns * 3 + li) * 220 + j + 110 - N_rb_dl];
+    grid[(((size_t)sf * N_ant + p) * 14 + sym) * nsc + 6 * j + (v + N_id_cell % 6) % 6] = crs[((size_t)ns * 3 + li) * 220 + j + 110 - N_rb_dl];
 }
 
 // symbols_to_samples_dl: bins 1..h <- subcarriers h..2h-1, bins N-h..N-1 <- subcarriers 0..h-1, unnormalised inverse DFT, cyclic prefix.
 // The inverse transform is conj(FFT(conj(X))) on the shared forward FFT.  out: [n_sf][samples per subframe] float2.
 __global__ void __launch_bounds__(512)
-ofdm_mod_kernel(const float2 *__restrict__ grid, int N, int cp0, int cpe, int nsc, const float2 *__restrict__ tw, float2 *__restrict__ out)
+ofdm_mod_kernel(const float2 *__restrict__ grid, int N, int cp0, int cpe, int nsc, const float2 *__restrict__ tw, float2 *__restrict__ out, int N_ant,
+                float4 gain_re, float4 gain_im)
 {
     extern __shared__ float2 sm_f2[];
     float2 *bufA = sm_f2, *bufB = sm_f2 + N;
     const int sf = blockIdx.x / 14, sym = blockIdx.x - sf * 14, h = nsc / 2;
-    const float2 *g = grid + ((size_t)sf * 14 + sym) * nsc;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        float2 v = make_float2(0.f, 0.f);
-        if (i >= 1 && i <= h) v = g[h + i - 1];
-        else if (i >= N - h) v = g[i - (N - h)];
-        bufA[i] = make_float2(v.x, -v.y);
-    }
-    __syncthreads();
-    const float2 *x = stockham_forward(bufA, bufB, N, tw);
     const int slot = sym / 7, l = sym % 7;
     const int cp = l == 0 ? cp0 : cpe;
     const long long base = (long long)sf * (14LL * N + 2LL * cp0 + 12LL * cpe) + (long long)slot * (7LL * N + cp0 + 6LL * cpe) +
                            (long long)l * (N + cpe) + (l > 0 ? cp0 - cpe : 0);
-    for (int i = threadIdx.x; i < N + cp; i += blockDim.x) {
-        const float2 v = x[i < cp ? N - cp + i : i - cp];
-        out[base + i] = make_float2(v.x, -v.y);
+    const float gr[4] = {gain_re.x, gain_re.y, gain_re.z, gain_re.w}, gi[4] = {gain_im.x, gain_im.y, gain_im.z, gain_im.w};
+    constexpr int MAX_PER_THREAD = 36;                       // (N + cp) / blockDim.x <= (2048 + 160) / 64
+    float2 acc[MAX_PER_THREAD];
+    for (int p = 0; p < N_ant; p++) {
+        const float2 *g = grid + (((size_t)sf * N_ant + p) * 14 + sym) * nsc;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            float2 v = make_float2(0.f, 0.f);
+            if (i >= 1 && i <= h) v = g[h + i - 1];
+            else if (i >= N - h) v = g[i - (N - h)];
+            bufA[i] = make_float2(v.x, -v.y);
+        }
+        __syncthreads();
+        const float2 *x = stockham_forward(bufA, bufB, N, tw);
+        int q = 0;
+        for (int i = threadIdx.x; i < N + cp; i += blockDim.x, q++) {
+            const float2 c = x[i < cp ? N - cp + i : i - cp];
+            const float2 v = make_float2(c.x, -c.y);
+            if (N_ant == 1 && gr[0] == 1.0f && gi[0] == 0.0f) { out[base + i] = v; continue; }     // one port, unit channel: the signal itself
+            // flat channel of port p, the ports add at the receiver
+            const float2 w = make_float2(__fsub_rn(__fmul_rn(gr[p], v.x), __fmul_rn(gi[p], v.y)), __fadd_rn(__fmul_rn(gr[p], v.y), __fmul_rn(gi[p], v.x)));
+            acc[q] = p == 0 ? w : make_float2(__fadd_rn(acc[q].x, w.x), __fadd_rn(acc[q].y, w.y));
+            if (p == N_ant - 1) out[base + i] = acc[q];
+        }
     }
 }
 
@@ -176,10 +215,21 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
                                          int N_rb_dl, int N_id_cell, int N_ant, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
                                          float *d_iq, void *stream_)
 {
-    if (!ctx || !d_tb_bits || !allocs || !subfr_num || n_sf < 1 || n_alloc < 1 || fs_idx < 0 || fs_idx > 4 || N_id_cell < 0 || N_id_cell > 503 ||
-        (!d_grid && !d_iq))
+    if (N_ant != 1) { if (ctx) lteb200_set_error(ctx, "dl_transmit_batch: one antenna port (lteb200_dl_transmit_frames_batch takes 2 and 4)"); return ctx ? LTEB200_ERR_UNSUPPORTED : LTEB200_ERR_ARGS; }
+    lteb200_tx_control ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    ctl.N_id_cell = N_id_cell; ctl.N_ant = 1; ctl.ant_gain_re[0] = 1.0f;
+    return lteb200_dl_transmit_frames_batch(ctx, d_tb_bits, tb_stride, allocs, n_alloc, fs_idx, N_rb_dl, &ctl, subfr_num, n_sf, N_pdcch_symbs, d_grid, d_iq, stream_);
+}
+
+extern "C" int lteb200_dl_transmit_frames_batch(lteb200_ctx *ctx, const uint8_t *d_tb_bits, int tb_stride, const lteb200_alloc *allocs, int n_alloc, int fs_idx,
+                                                int N_rb_dl, const lteb200_tx_control *ctl, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
+                                                float *d_iq, void *stream_)
+{
+    if (!ctx || !ctl || !subfr_num || n_sf < 1 || n_alloc < 0 || (n_alloc > 0 && (!d_tb_bits || !allocs)) || fs_idx < 0 || fs_idx > 4 || (!d_grid && !d_iq))
         return LTEB200_ERR_ARGS;
-    if (N_ant != 1) { lteb200_set_error(ctx, "dl_transmit: one antenna port only"); return LTEB200_ERR_UNSUPPORTED; }
+    const int N_id_cell = ctl->N_id_cell, N_ant = ctl->N_ant;
+    if (N_id_cell < 0 || N_id_cell > 503 || !(N_ant == 1 || N_ant == 2 || N_ant == 4)) return LTEB200_ERR_ARGS;
     if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     const int N = 128 << fs_idx, nsc = 12 * N_rb_dl;
     if (nsc >= N) { lteb200_set_error(ctx, "dl_transmit: N_rb_dl does not fit the sample rate"); return LTEB200_ERR_ARGS; }
@@ -187,19 +237,24 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
     cudaStream_t stream = (cudaStream_t)stream_;
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(g_tx_mu);
+    StreamScope scope;
     float2 *grid = (float2 *)d_grid;
-    if (!grid) LTE_CUDA_OK(ctx, cudaMallocAsync(&grid, sizeof(float2) * 14 * nsc * (size_t)n_sf, stream));
+    const size_t ps = (size_t)14 * nsc, sfs = ps * N_ant;
+    if (!grid) LTE_CUDA_OK(ctx, scope.alloc(&grid, sizeof(float2) * sfs * (size_t)n_sf, stream));
     int *d_sn = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_sn, sizeof(int) * n_sf, stream));
     int rc = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream);
-    auto release = [&]() { cudaFreeAsync(d_sn, stream); if (!d_grid) cudaFreeAsync(grid, stream); };
-    if (rc) { release(); return rc; }
-    LTE_CUDA_OK(ctx, cudaMemsetAsync(grid, 0, sizeof(float2) * 14 * nsc * (size_t)n_sf, stream));
+    if (rc) return rc;
+    LTE_CUDA_OK(ctx, cudaMemsetAsync(grid, 0, sizeof(float2) * sfs * (size_t)n_sf, stream));
     float2 *crs = nullptr;
     rc = get_crs_table(ctx, N_id_cell, &crs);
-    if (rc) { release(); return rc; }
-    crs_map_kernel<<<dim3(ceil_div(8 * N_rb_dl, 128), n_sf), 128, 0, stream>>>(crs, d_sn, N_rb_dl, N_id_cell, nsc, grid);
+    if (rc) return rc;
+    crs_map_kernel<<<dim3(ceil_div(8 * N_rb_dl, 128), n_sf, N_ant), 128, 0, stream>>>(crs, d_sn, N_rb_dl, N_id_cell, nsc, N_ant, grid);
     ctx->launches += 1;
+    if (ctl->sync || ctl->pbch || ctl->pdcch) {
+        rc = control_tx_launch(ctx, grid, sfs, ps, d_sn, subfr_num, n_sf, N_rb_dl, N_pdcch_symbs - (N_rb_dl <= 10 ? 1 : 0), ctl, allocs, n_alloc, stream);
+        if (rc) return rc;
+    }
     const uint32_t *crc_tab = nullptr;
     rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
     // transport blocks: groups of up to 8 allocations with the same code block size share a launch
@@ -210,6 +265,8 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
             lteb200_set_error(ctx, "dl_transmit: TBS %d needs filler bits (K = %d), which the reference's encoder does not produce", allocs[a].tbs, T[a].K);
             rc = LTEB200_ERR_UNSUPPORTED;
         }
+        for (int c = 0; c < 3 && rc == LTEB200_OK; c++)
+            if (T[a].M[c] % N_ant) { lteb200_set_error(ctx, "dl_transmit: allocation %d is not a whole number of transmit-diversity groups", a); rc = LTEB200_ERR_UNSUPPORTED; }
         if (rc == LTEB200_OK && tb_stride < allocs[a].tbs) rc = LTEB200_ERR_ARGS;
     }
     for (int a = 0; a < n_alloc && rc == LTEB200_OK;) {
@@ -241,7 +298,7 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
             e++;
         }
         if (rc) break;
-        P.n_al = e - a; P.n_sf = n_sf; P.n_alloc_total = n_alloc; P.tb_stride = tb_stride; P.nsc = nsc; P.K = K;
+        P.n_al = e - a; P.n_sf = n_sf; P.n_alloc_total = n_alloc; P.tb_stride = tb_stride; P.nsc = nsc; P.K = K; P.N_ant = N_ant;
         P.subfr_num = d_sn; P.tb = d_tb_bits; P.pi = qt.pi; P.crc_tab = crc_tab; P.grid = grid;
         const size_t smem = (size_t)K + 3 * (K + 4);
         dlsch_encode_kernel<<<P.n_al * n_sf, 256, smem, stream>>>(P);
@@ -253,11 +310,12 @@ extern "C" int lteb200_dl_transmit_batch(lteb200_ctx *ctx, const uint8_t *d_tb_b
         rc = get_twiddles(ctx, N, &tw);
         if (rc == LTEB200_OK) {
             const int threads = N / 4 < 64 ? 64 : (N / 4 > 512 ? 512 : N / 4);
-            ofdm_mod_kernel<<<n_sf * 14, threads, sizeof(float2) * 2 * N, stream>>>(grid, N, 10 << fs_idx, 9 << fs_idx, nsc, tw, (float2 *)d_iq);
+            const float4 g_re = make_float4(ctl->ant_gain_re[0], ctl->ant_gain_re[1], ctl->ant_gain_re[2], ctl->ant_gain_re[3]);
+            const float4 g_im = make_float4(ctl->ant_gain_im[0], ctl->ant_gain_im[1], ctl->ant_gain_im[2], ctl->ant_gain_im[3]);
+            ofdm_mod_kernel<<<n_sf * 14, threads, sizeof(float2) * 2 * N, stream>>>(grid, N, 10 << fs_idx, 9 << fs_idx, nsc, tw, (float2 *)d_iq, N_ant, g_re, g_im);
             ctx->launches += 1;
         }
     }
     if (rc == LTEB200_OK) LTE_CUDA_OK(ctx, cudaGetLastError());
-    release();
     return rc;
 }

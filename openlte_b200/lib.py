@@ -95,6 +95,8 @@ SYMBOLS = {
     "lteb200_q8_stride": (C.c_size_t, [_i]),
     "lteb200_pdsch_llr_q8_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_turbo_decode_q8_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "lteb200_dci_1a_tbs": (_i, [_i]),
+    "lteb200_dl_transmit_frames_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "lteb200_dl_transmit_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "lteb200_freq_shift_batch": (_i, [_vp, _vp, _i, _ll, _ll, _f, _i, _vp, _vp]),
     "lteb200_freq_shift": (_i, [_vp, _vp, _vp, _u32, _u32, _f, _i]),
@@ -102,6 +104,12 @@ SYMBOLS = {
     "lteb200_prs_c_batch": (_i, [_vp, _u32, _i, _vp, _vp]),
     "lteb200_crc24a_check_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
 }
+
+
+class TxControl(C.Structure):
+    """lteb200_tx_control (include/lte_b200.h)"""
+    _fields_ = [("N_id_cell", C.c_int32), ("N_ant", C.c_int32), ("ant_gain_re", C.c_float * 4), ("ant_gain_im", C.c_float * 4), ("sync", C.c_int32),
+                ("pbch", C.c_int32), ("sfn_first", C.c_int32), ("mib_bits", C.c_void_p), ("pdcch", C.c_int32), ("phich_res", C.c_float), ("mcs", C.c_int32 * 8)]
 
 
 class Lib:

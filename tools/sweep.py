@@ -37,8 +37,16 @@ def plan(n_rb, mod, cell, cfi):
 
 
 def main():
+    """Single process: one GPU.  Under torchrun (BASELINE config 5: 8 x B200) every rank sweeps its own GPU with its own data -- the chain has no
+    inter-GPU dependency -- and rank 0 prints whole-job subframes/s: all ranks' subframes over the slowest rank's device time."""
     n_sf = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    L = openlte_b200.load(); ctx = L.new_ctx(0)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = openlte_b200.load(); ctx = L.new_ctx(local)
     cell, cfi = 42, 2
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     configs = [(bw, n_rb, fs_idx, mname, mod, None) for bw, (n_rb, fs_idx) in BW.items() for mname, mod in MODS.items()]
@@ -50,7 +58,7 @@ def main():
             K, groups = forced if forced else plan(n_rb, mod, cell, cfi)
             allocs = [dict(mod=mod, prb=g, tbs=K - 24, rnti=0x300 + i) for i, g in enumerate(groups)]
             seg = 20
-            tx = synth.make_subframes(seg, allocs, N_id_cell=cell, N_rb_dl=n_rb, fs_idx=fs_idx, cfi=cfi, seed=7, first_subfr=1)
+            tx = synth.make_subframes(seg, allocs, N_id_cell=cell, N_rb_dl=n_rb, fs_idx=fs_idx, cfi=cfi, seed=7 + rank, first_subfr=1)
             n_s = 1920 << fs_idx
             stream = np.tile(tx["samples"].reshape(-1), -(-n_sf // seg))[: n_sf * n_s]
             stream = np.concatenate([stream, synth.crs_only_tail(n_rb, cell, (1 + n_sf) % 10, fs_idx)[: 4 * (128 << fs_idx)]])
@@ -73,11 +81,21 @@ def main():
                     run()
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 3
+                if world > 1:
+                    t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
                 want = np.stack(tx["tb"], 1)[np.arange(n_sf) % seg]
-                res[name] = dict(ms_per_step=round(ms, 3), subframes_per_s=round(n_sf / ms * 1e3, 1), crc_pass=float(ok.float().mean().item()),
-                                 bits_ok=bool(np.array_equal(tb.cpu().numpy(), want)))
-            print(json.dumps(dict(bandwidth_MHz=bw, N_rb_dl=n_rb, modulation=mname, n_alloc=len(allocs), prb_per_alloc=len(groups[0]), K=K, n_sf=n_sf, **res)), flush=True)
+                okf = torch.tensor([float(ok.float().mean().item()), float(np.array_equal(tb.cpu().numpy(), want))], device="cuda")
+                if world > 1:
+                    dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+                res[name] = dict(ms_per_step=round(ms, 3), subframes_per_s=round(world * n_sf / ms * 1e3, 1), crc_pass=float(okf[0].item()),
+                                 bits_ok=bool(okf[1].item() == 1.0))
+            if rank == 0:
+                print(json.dumps(dict(bandwidth_MHz=bw, N_rb_dl=n_rb, modulation=mname, n_alloc=len(allocs), prb_per_alloc=len(groups[0]), K=K, n_sf_per_gpu=n_sf, n_gpus=world,
+                                      **res)), flush=True)
 
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
