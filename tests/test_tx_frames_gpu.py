@@ -95,7 +95,9 @@ def test_generated_stream_through_the_scan_path(ctx, lib):
     bits = out.cpu().numpy()
     for b in range(n_sf):
         r = res[b]
-        assert r.cfi == cfi and r.N_alloc == n_alloc, f"subframe {b}: cfi {r.cfi}, {r.N_alloc} allocations (pdcch_err {r.pdcch_err})"
+        # (a DCI whose neighbouring CCEs are empty is found again at aggregation level 8, exactly as the reference's blind decoder finds the
+        # shipped capture's SIB1 twice: at least n_alloc entries, every allocation among them)
+        assert r.cfi == cfi and r.N_alloc >= n_alloc, f"subframe {b}: cfi {r.cfi}, {r.N_alloc} allocations (pdcch_err {r.pdcch_err})"
         seen = set()
         for k in range(r.N_alloc):
             d = r.dci[k]
