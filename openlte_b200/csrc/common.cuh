@@ -53,6 +53,7 @@ struct lteb200_ctx {
     float        cfo_hz;       // front-end frequency shift fused into the OFDM sample load (0 = off)
     long long    cfo_base;
     int          demap;        // LTEB200_DEMAP_* for the max-log-MAP receive path
+    int          tb_packed;    // LTEB200_TB_*
     // pinned, device-mapped ring for small per-call parameter arrays (see lteb200_upload_small)
     char        *ring_h, *ring_d;
     size_t       ring_bytes, ring_off;

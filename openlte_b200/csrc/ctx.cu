@@ -37,6 +37,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->ring_h = c->ring_d = nullptr; c->ring_bytes = c->ring_off = 0;
     c->cfo_hz = 0.f; c->cfo_base = 0;
     c->demap = LTEB200_DEMAP_REFERENCE;
+    c->tb_packed = LTEB200_TB_BYTES;
     c->s_h2d = c->s_comp = c->s_d2h = c->s_front = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
@@ -64,6 +65,13 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     for (auto &kv : c->mlm2) cudaFree(kv.second);
     for (auto &kv : c->rum) { cudaFree(kv.second.first_k); cudaFree(kv.second.first_kT); }
     delete c;
+}
+
+extern "C" int lteb200_set_tb_format(lteb200_ctx *c, int format)
+{
+    if (!c || (format != LTEB200_TB_BYTES && format != LTEB200_TB_PACKED)) return LTEB200_ERR_ARGS;
+    c->tb_packed = format;
+    return LTEB200_OK;
 }
 
 extern "C" int lteb200_set_demapper(lteb200_ctx *c, int demap)

@@ -296,7 +296,7 @@ static int q8_common(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
     if (rc) return rc;
     if (e != n_alloc) return LTEB200_ERR_UNSUPPORTED;
     fp.N_ant = N_ant; fp.nsc = 12 * N_rb_dl; fp.n_alloc_total = n_alloc;
-    fp.demap = ctx->demap; fp.vshift = N_id_cell % 6;
+    fp.demap = ctx->demap; fp.vshift = N_id_cell % 6; fp.tb_packed = ctx->tb_packed;
     return LTEB200_OK;
 }
 
@@ -332,13 +332,15 @@ extern "C" int lteb200_turbo_decode_q8_batch(lteb200_ctx *ctx, const int8_t *d_q
     for (int a = 0; a < n_alloc; a++) {
         int Ka = 0, Fa = 0;
         if (seg_params(allocs[a].tbs, &Ka, &Fa) || Ka != K) { lteb200_set_error(ctx, "q8 decoder: transport block size %d does not map onto K=%d", allocs[a].tbs, K); return LTEB200_ERR_ARGS; }
-        if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+        if (tb_stride < (ctx->tb_packed ? (allocs[a].tbs + 7) / 8 : allocs[a].tbs)) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+        if (ctx->tb_packed && Fa != 0) { lteb200_set_error(ctx, "packed transport-block output needs tbs + 24 = K"); return LTEB200_ERR_UNSUPPORTED; }
         fp.al[a].F = Fa; fp.al[a].tbs = allocs[a].tbs; fp.al[a].a_idx = a;
     }
     const uint32_t *crc_tab = nullptr;
     int rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
     if (rc) return rc;
     fp.crc_tab = crc_tab; fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride; fp.n_al = n_alloc;
+    fp.tb_packed = ctx->tb_packed;
     return turbo_mlm2_launch(ctx, nullptr, d_q8, K, n_cb, n_iter, nullptr, &fp, (cudaStream_t)stream_);
 }
 
@@ -365,7 +367,11 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
     for (int a = 0; a < n_alloc; a++) {
         rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[a], &T[a]);
         if (rc) return rc;
-        if (tb_stride < allocs[a].tbs) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+        if (tb_stride < (ctx->tb_packed ? (allocs[a].tbs + 7) / 8 : allocs[a].tbs)) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
+        if (ctx->tb_packed && (T[a].F != 0 || !mlm2_handles(T[a].K) || turbo_mode != LTEB200_TURBO_MAXLOGMAP)) {
+            lteb200_set_error(ctx, "packed transport-block output: max-log-MAP path, block sizes that are multiples of 32, no filler bits (tbs + 24 = K)");
+            return LTEB200_ERR_UNSUPPORTED;
+        }
     }
     // ---- fused path: one kernel per group of allocations with equal K does demod + unmatch + decode + CRC per transport block
     bool fusable = turbo_mode == LTEB200_TURBO_MAXLOGMAP && !getenv("LTEB200_NO_FUSE");
@@ -390,7 +396,7 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
             memset(&fp, 0, sizeof(fp));
             fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.crc_tab = crc_tab;
             fp.N_ant = N_ant;
-            fp.demap = ctx->demap; fp.vshift = N_id_cell % 6;
+            fp.demap = ctx->demap; fp.vshift = N_id_cell % 6; fp.tb_packed = ctx->tb_packed;
             fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
             int e = a;
             rc = fill_group(ctx, T, allocs, n_alloc, a, &e, fp);

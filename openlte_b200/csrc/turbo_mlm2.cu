@@ -511,7 +511,15 @@ turbo_mlm2_kernel(const void *__restrict__ in, int K, int n_iter, const uint16_t
         if (active) {
             const int idx0 = k0 - A.F;                                     // index of this thread's first bit inside [a | p]
             const bool fast = idx0 >= 0 && idx0 + 2 * WIN <= A.tbs && (((size_t)(o + idx0)) & 7) == 0;
-            if (fast) {
+            if (fp.tb_packed) {
+                // eight bits per byte, first bit in the MSB (the launcher admits this format only without filler bits: idx0 = k0, 32 | k0)
+                const uint32_t w = __byte_perm(__brev(bits), 0, 0x0123);   // message bit k0 + j -> byte j / 8, bit 7 - j % 8
+                uint8_t *ob = o + (idx0 >> 3);
+                if (idx0 + 2 * WIN <= A.tbs && (((size_t)ob) & 3) == 0) *reinterpret_cast<uint32_t *>(ob) = w;
+                else
+                    for (int j = 0; j < 4; j++)
+                        if (idx0 + 8 * j < A.tbs) ob[j] = (uint8_t)(w >> (8 * j));    // transport block sizes are multiples of 8
+            } else if (fast) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t b0 = (bits >> (8 * j)) & 0xfu, b1 = (bits >> (8 * j + 4)) & 0xfu;

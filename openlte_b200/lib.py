@@ -92,6 +92,7 @@ SYMBOLS = {
     "lteb200_pdcch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _u32, C.c_uint8, _f, _i, _vp, _vp, _vp, _vp]),
     "lteb200_dl_scan_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
     "lteb200_set_demapper": (_i, [_vp, _i]),
+    "lteb200_set_tb_format": (_i, [_vp, _i]),
     "lteb200_q8_stride": (C.c_size_t, [_i]),
     "lteb200_pdsch_llr_q8_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_turbo_decode_q8_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
