@@ -76,21 +76,48 @@ chan_est_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const int *
         Ag[i * 1200 + k] = atan2f(ti, tr);
     }
     __syncthreads();
-    // 2. sequential phase unwrap along frequency
-    if (threadIdx.x < N_sym) {
-        const int i = threadIdx.x;
-        float *A = Ag + i * 1200;
-        const int of = crs_off(p, i, vsh);
-        float prev = A[of];
-        // eight tones per round: loads first, then the dependent chain on registers, then the stores (no shared-memory latency on the chain)
-        for (int j0 = 1; j0 < n_crs; j0 += 8) {
-            float v[8];
+    // 2. phase unwrap along frequency (liblte_phy.cc:6033-6036: every tone is brought within pi of its already unwrapped predecessor by adding or
+    // subtracting 2 pi, in float, one turn at a time).  The number of turns applied to tone j is the running sum of the turns between neighbours,
+    // d_j = -1 / 0 / +1 according to whether the RAW difference A[j] - A[j-1] is >= pi, in between, or <= -pi: a prefix sum instead of a chain of
+    // 2 N_rb dependent steps.  One warp per CRS symbol, seven tones per lane; the turns are then applied to the raw value one at a time, which
+    // reproduces the reference's sequence of float roundings.  (A decision can differ from the sequential form only when a difference lies within
+    // an ulp of pi -- where the reference's own result is arbitrary.)  The round-1 kernel spent 43 % of its warp samples here, 251 of 256 threads
+    // waiting at the barrier behind five (profiles/r2_chain_ncu_summary.json).
+    {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (w < N_sym) {
+            float *A = Ag + w * 1200;
+            const int of = crs_off(p, w, vsh);
+            constexpr int PER = 7;                                   // 32 x 7 = 224 >= 2 x 100 tones
+            const float PI_UP = __uint_as_float(0x40490FDBu);
+            const int j0 = lane * PER;
+            float v[PER + 1];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = (j0 + u < n_crs) ? A[6 * (j0 + u) + of] : 0.f;
+            for (int u = 0; u <= PER; u++) { const int j = j0 - 1 + u; v[u] = (j >= 0 && j < n_crs) ? A[6 * j + of] : 0.f; }
+            int d[PER], tot = 0;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (j0 + u < n_crs) { prev = wrap_phase(v[u], prev); v[u] = prev; }
+            for (int u = 0; u < PER; u++) {
+                const int j = j0 + u;
+                int t = 0;
+                if (j >= 1 && j < n_crs) { const float df = __fsub_rn(v[u + 1], v[u]); t = df >= PI_UP ? -1 : (df <= -PI_UP ? 1 : 0); }
+                tot += t; d[u] = tot;                                 // inclusive within the lane
+            }
+            int excl = tot;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (j0 + u < n_crs) A[6 * (j0 + u) + of] = v[u];
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, excl, o); if (lane >= o) excl += x; }
+            excl -= tot;
+            __syncwarp();                                             // every raw value has been read
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int j = j0 + u;
+                if (j >= 1 && j < n_crs) {
+                    int k = excl + d[u];
+                    float ph = v[u + 1];
+                    for (; k < 0; k++) ph = (float)((double)ph - 2 * PI_D);
+                    for (; k > 0; k--) ph = (float)((double)ph + 2 * PI_D);
+                    A[6 * j + of] = ph;
+                }
+            }
         }
     }
     __syncthreads();

@@ -163,7 +163,7 @@ def test_north_star_load_soft_decisions_beat_hard_decisions(ctx, lib):
                     lib.set_demapper(ctx.h, 0)
                 okh = ok.cpu().numpy() == 1
                 good = (tb.cpu().numpy() == want).all(axis=2)
-                assert np.array_equal(okh, good), "CRC verdict and bit equality disagree"
-                fails[noise][demap] += int((~good).sum())
+                assert good[okh].all(), "a CRC passed on wrong bits"        # (the converse need not hold: an error confined to the 24 parity bits)
+                fails[noise][demap] += int((~okh).sum())
     assert fails[0.0] == {0: 0, 1: 0}
     assert fails[1.6][0] >= 20 and 2 * fails[1.6][1] <= fails[1.6][0], f"failures of 96 blocks at 25 dB: hard {fails[1.6][0]}, soft {fails[1.6][1]}"
