@@ -49,7 +49,7 @@ def test_packed_equals_packbits_of_bytes(ctx, lib):
         assert np.array_equal(h_ok.numpy(), okw)
         # refused: reference-exact decoder, and a block size with filler bits / not a multiple of 32
         assert lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), 4, cfi, ca, 3, 0, 8, dptr(tbp), 768, dptr(ok2), stream_ptr()) == -4
-        odd = (Alloc * 1)(Alloc.make(1, list(range(0, 10)), 456, 0x9))          # K = 480: not a multiple of 32
+        odd = (Alloc * 1)(Alloc.make(1, list(range(0, 10)), 464, 0x9))          # K = 488: not a multiple of 32
         assert lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), 4, cfi, odd, 1, 1, 8, dptr(tbp), 768, dptr(ok2), stream_ptr()) == -4
     finally:
         lib.set_tb_format(ctx.h, 0)
