@@ -84,6 +84,15 @@ ofdm_demod_kernel(const T *__restrict__ iq, long long n_samps, const long long *
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mulmj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
+// complex product with fused multiply-adds (this kernel is held to a tolerance, not to the bit pattern of the oracle's FFT: the fused form is the
+// more accurate one and is four instructions instead of six)
+__device__ __forceinline__ float2 cmulf(float2 a, float2 w)
+{
+    return make_float2(__fmaf_rn(a.x, w.x, -__fmul_rn(a.y, w.y)), __fmaf_rn(a.x, w.y, __fmul_rn(a.y, w.x)));
+}
+// a * (1 - j) / sqrt(2) and a * (-1 - j) / sqrt(2): two additions and two products
+__device__ __forceinline__ float2 mul_w8_1(float2 a) { const float r = 0.70710678118654752440f; return make_float2(__fmul_rn(r, a.x + a.y), __fmul_rn(r, a.y - a.x)); }
+__device__ __forceinline__ float2 mul_w8_3(float2 a) { const float r = 0.70710678118654752440f; return make_float2(__fmul_rn(r, a.y - a.x), -__fmul_rn(r, a.x + a.y)); }
 
 template <int R> struct Dft;
 template <> struct Dft<4> {
@@ -98,9 +107,7 @@ template <> struct Dft<8> {
     {
         float2 e[4] = {x[0], x[2], x[4], x[6]}, o[4] = {x[1], x[3], x[5], x[7]};
         Dft<4>::run(e); Dft<4>::run(o);
-        const float r = 0.70710678118654752440f;
-        const float2 w1 = make_float2(r, -r), w3 = make_float2(-r, -r);
-        const float2 o1 = cmul(o[1], w1), o2 = mulmj(o[2]), o3 = cmul(o[3], w3);
+        const float2 o1 = mul_w8_1(o[1]), o2 = mulmj(o[2]), o3 = mul_w8_3(o[3]);
         x[0] = cadd(e[0], o[0]); x[4] = csub(e[0], o[0]);
         x[1] = cadd(e[1], o1);   x[5] = csub(e[1], o1);
         x[2] = cadd(e[2], o2);   x[6] = csub(e[2], o2);
@@ -120,7 +127,7 @@ template <> struct Dft<16> {
                              make_float2(0.f, -1.f), make_float2(-s1, -c1), make_float2(-r, -r), make_float2(-c1, -s1)};
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float2 t = (k == 0) ? o[0] : ((k == 4) ? mulmj(o[4]) : cmul(o[k], w[k]));
+            const float2 t = (k == 0) ? o[0] : ((k == 4) ? mulmj(o[4]) : ((k == 2) ? mul_w8_1(o[2]) : ((k == 6) ? mul_w8_3(o[6]) : cmulf(o[k], w[k]))));
             x[k] = cadd(e[k], t); x[k + 8] = csub(e[k], t);
         }
     }
@@ -132,7 +139,7 @@ template <> struct Dft<16> {
 // PAD_SRC / PAD_DST: the shared buffer is indexed through pad16() (one spare element per 16): the first pass writes 16 consecutive
 // elements per thread, which without the padding puts every lane of a warp on the same banks.
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
-template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID, bool CFO = false, bool PAD_SRC = false, bool PAD_DST = false>
+template <int N, int R, int n, typename T, bool SRC_GLOBAL, bool DST_GRID, bool CFO = false, bool PAD_SRC = false, bool PAD_DST = false, bool CHECK = true>
 __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long long w0, long long n_samps, const float2 *__restrict__ src,
                                               float2 *__restrict__ dst, const float2 *__restrict__ tw, float2 *__restrict__ out, int h, int tid,
                                               float cfo_hz = 0.f, double cfo_fs = 1.0, long long cfo_base = 0)
@@ -148,7 +155,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
             const int i = q + s * (p + n1 * k);
             if (SRC_GLOBAL) {
                 const long long sidx = w0 + i;
-                x[k] = (sidx >= 0 && sidx < n_samps) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
+                x[k] = (!CHECK || (sidx >= 0 && sidx < n_samps)) ? load_iq<T>(iq, sidx) : make_float2(0.f, 0.f);
                 if (CFO) x[k] = cfo_rotate(x[k], cfo_base + sidx, cfo_hz, cfo_fs);
             } else x[k] = src[PAD_SRC ? pad16(i) : i];
         }
@@ -160,7 +167,7 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
                 if (bin >= 1 && bin <= h) out[h + bin - 1] = x[k];
                 else if (bin >= N - h) out[bin - (N - h)] = x[k];
             } else {
-                const float2 v = (k == 0 || p == 0) ? x[k] : cmul(x[k], __ldg(&tw[p * k * s]));
+                const float2 v = (k == 0 || p == 0) ? x[k] : cmulf(x[k], __ldg(&tw[p * k * s]));
                 dst[PAD_DST ? pad16(q + s * (R * p + k)) : q + s * (R * p + k)] = v;
             }
         }
@@ -180,30 +187,31 @@ ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long lo
                          (l == 0 ? P.cp0 : P.cpe) - 1;
     float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
     const bool act = tid < N / 16;
+    const bool inb = w0 >= 0 && w0 + N <= n_samps;          // whole window inside the stream (all but the edges of a capture): no per-sample test
     if constexpr (N == 2048) {          // 16 x 16 x 8
-        if (act) stockham_pass<N, 16, 2048, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) { if (inb) stockham_pass<N, 16, 2048, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 2048, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
         if (act) stockham_pass<N, 16, 128, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 1024) {   // 16 x 16 x 4
-        if (act) stockham_pass<N, 16, 1024, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) { if (inb) stockham_pass<N, 16, 1024, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 1024, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
         if (act) stockham_pass<N, 16, 64, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 512) {    // 16 x 8 x 4
-        if (act) stockham_pass<N, 16, 512, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) { if (inb) stockham_pass<N, 16, 512, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 512, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
         if (act) stockham_pass<N, 8, 32, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
         __syncthreads();
         if (act) stockham_pass<N, 4, 4, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
     } else if constexpr (N == 256) {    // 16 x 16
-        if (act) stockham_pass<N, 16, 256, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) { if (inb) stockham_pass<N, 16, 256, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 256, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
         if (act) stockham_pass<N, 16, 16, T, false, true, false, true, false>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     } else {                  // 128 = 16 x 8
-        if (act) stockham_pass<N, 16, 128, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base);
+        if (act) { if (inb) stockham_pass<N, 16, 128, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 128, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
         if (act) stockham_pass<N, 8, 8, T, false, true, false, true, false>(iq, w0, n_samps, bufA, nullptr, tw, out, P.h, tid);
     }

@@ -39,7 +39,9 @@ def plan(n_rb, mod, cell, cfi):
 def main():
     """Single process: one GPU.  Under torchrun (BASELINE config 5: 8 x B200) every rank sweeps its own GPU with its own data -- the chain has no
     inter-GPU dependency -- and rank 0 prints whole-job subframes/s: all ranks' subframes over the slowest rank's device time."""
-    n_sf = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    argv = [a for a in sys.argv[1:] if a != "--stages"]
+    want_stages = "--stages" in sys.argv          # per-stage device times (CUDA events) of the max-log-MAP chain, per configuration
+    n_sf = int(argv[0]) if argv else 2000
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
@@ -89,6 +91,39 @@ def main():
                     dist.all_reduce(okf, op=dist.ReduceOp.MIN)
                 res[name] = dict(ms_per_step=round(ms, 3), subframes_per_s=round(world * n_sf / ms * 1e3, 1), crc_pass=float(okf[0].item()),
                                  bits_ok=bool(okf[1].item() == 1.0))
+            if want_stages and rank == 0:
+                nsc = 12 * n_rb
+                grid = torch.zeros((n_sf, 16, nsc, 2), dtype=torch.float32, device="cuda"); ce = torch.zeros((n_sf, 1, 14, nsc, 2), dtype=torch.float32, device="cuda")
+                vp = lambda t_: C.c_void_p(t_.data_ptr())
+
+                def t_of(fn, reps=3):
+                    fn(); torch.cuda.synchronize()
+                    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(reps):
+                        fn()
+                    b.record(); torch.cuda.synchronize()
+                    return round(a.elapsed_time(b) / reps, 4)
+                st = {}
+                st["ofdm_demod"] = t_of(lambda: ctx.check(L.ofdm_demod_batch(ctx.h, vp(d_iq), 1, iq.shape[0], fs_idx, n_rb, p(start), n_sf, vp(grid), None)))
+                st["chan_est"] = t_of(lambda: ctx.check(L.chan_est_batch(ctx.h, vp(grid), p(sn), n_rb, cell, 1, n_sf, vp(ce), None)))
+                stride = int(L.q8_stride(K))
+                if stride:
+                    # (the stage entry points take at most 8 allocations per call)
+                    groups8 = [list(range(g, min(g + 8, len(allocs)))) for g in range(0, len(allocs), 8)]
+                    cas = [(Alloc * len(g))(*[ca[i] for i in g]) for g in groups8]
+                    q8s = [torch.zeros((n_sf * len(g), stride), dtype=torch.int8, device="cuda") for g in groups8]
+                    tbs_ = [torch.zeros((n_sf, len(g), K - 24), dtype=torch.uint8, device="cuda") for g in groups8]
+                    oks_ = [torch.zeros((n_sf, len(g)), dtype=torch.int32, device="cuda") for g in groups8]
+                    st["pdsch_llr_q8"] = t_of(lambda: [ctx.check(L.pdsch_llr_q8_batch(ctx.h, vp(grid), vp(ce), n_rb, cell, 1, p(sn), n_sf, cfi, cas[i], len(g), vp(q8s[i]), None))
+                                                       for i, g in enumerate(groups8)])
+                    st["turbo_mlm2"] = t_of(lambda: [ctx.check(L.turbo_decode_q8_batch(ctx.h, vp(q8s[i]), K, n_sf * len(g), 8, cas[i], len(g), n_sf, vp(tbs_[i]), K - 24, vp(oks_[i]), None))
+                                                     for i, g in enumerate(groups8)])
+                else:
+                    st["pdsch_decode (fused window-per-thread kernel: K is not a multiple of 32)"] = t_of(lambda: ctx.check(
+                        L.pdsch_decode_batch(ctx.h, vp(grid), vp(ce), n_rb, cell, 1, p(sn), n_sf, cfi, ca, len(allocs), 1, 8, vp(tb), K - 24, vp(ok), None)))
+                st["sum"] = round(sum(st.values()), 4)
+                res["stages_ms_maxlogmap"] = st
             if rank == 0:
                 print(json.dumps(dict(bandwidth_MHz=bw, N_rb_dl=n_rb, modulation=mname, n_alloc=len(allocs), prb_per_alloc=len(groups[0]), K=K, n_sf_per_gpu=n_sf, n_gpus=world,
                                       **res)), flush=True)
