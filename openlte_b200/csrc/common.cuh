@@ -32,6 +32,7 @@ struct QppTables {
 struct RateUnmatchMap {
     int32_t *first_k;    // [3*(K+4)] first e index feeding output d[3i+x], or -1
     int32_t *first_kT;   // [3][16 NT] the same in window-transposed order (position (k mod 16) NT + k/16; -1 on padding) + [12] tail + [4] pad
+    uint16_t *inv_kT;    // [period] inverse of first_kT: image position fed by e-bit k of the first lap
     int      n_nonnull;  // period of the circular buffer in e indices
 };
 

@@ -63,7 +63,7 @@ extern "C" void lteb200_destroy(lteb200_ctx *c)
     for (auto &kv : c->qpp) { cudaFree(kv.second.pi); cudaFree(kv.second.inv_last); }
     for (auto &kv : c->mlm) cudaFree(kv.second.piT);   // one blob: piT | csr_start | csr_pos
     for (auto &kv : c->mlm2) cudaFree(kv.second);
-    for (auto &kv : c->rum) { cudaFree(kv.second.first_k); cudaFree(kv.second.first_kT); }
+    for (auto &kv : c->rum) { cudaFree(kv.second.first_k); cudaFree(kv.second.first_kT); cudaFree(kv.second.inv_kT); }
     delete c;
 }
 

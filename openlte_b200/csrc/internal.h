@@ -11,6 +11,7 @@ struct AllocTables {
     int idx_stride;
     int M[3];
     uint8_t *cseq;    // [10][c_stride]
+    uint8_t *cseqP;   // [10][idx_stride]: the Qm scrambling bits of a resource element in one byte (bit q = bit q of the element)
     int c_stride;
     int Qm, K, F;
 };

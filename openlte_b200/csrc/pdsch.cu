@@ -191,8 +191,14 @@ int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
     std::vector<uint8_t> cs(10 * (size_t)t.c_stride);
     for (int sn = 0; sn < 10; sn++)   // c_init = rnti<<14 | q<<13 | subframe<<9 | N_id_cell, liblte_phy.cc:3831
         prs_c_host(((uint32_t)al.rnti << 14) | ((uint32_t)sn << 9) | (uint32_t)N_id_cell, t.c_stride, cs.data() + (size_t)sn * t.c_stride);
+    std::vector<uint8_t> csp(10 * (size_t)t.idx_stride, 0);
+    for (int sn = 0; sn < 10; sn++)
+        for (int r = 0; r < t.idx_stride; r++)
+            for (int q = 0; q < t.Qm; q++) csp[(size_t)sn * t.idx_stride + r] |= (uint8_t)(cs[(size_t)sn * t.c_stride + (size_t)r * t.Qm + q] << q);
     LTE_CUDA_OK(ctx, cudaMalloc(&t.re_idx, sizeof(int) * flat.size()));
     LTE_CUDA_OK(ctx, cudaMalloc(&t.cseq, cs.size()));
+    LTE_CUDA_OK(ctx, cudaMalloc(&t.cseqP, csp.size()));
+    LTE_CUDA_OK(ctx, cudaMemcpy(t.cseqP, csp.data(), csp.size(), cudaMemcpyHostToDevice));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.re_idx, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.cseq, cs.data(), cs.size(), cudaMemcpyHostToDevice));
     g_alloc_tabs[key] = t;
@@ -264,7 +270,7 @@ static int fill_group(lteb200_ctx *ctx, const std::vector<AllocTables> &T, const
         int rc = rate_unmatch_get_map(ctx, T[e].K + 4, 0, 1, allocs[e].tx_mode, 250368, 8, 0, allocs[e].rv_idx, &m);   // M_dl_harq 8, cat-1 N_soft: liblte_phy.cc:3843-3844
         if (rc) return rc;
         FusedAlloc &A = fp.al[e - a];
-        A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.first_k = m.first_k; A.first_kT = m.first_kT; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
+        A.re_idx = T[e].re_idx; A.cseq = T[e].cseq; A.cseqP = T[e].cseqP; A.first_k = m.first_k; A.first_kT = m.first_kT; A.inv_kT = m.inv_kT; A.idx_stride = T[e].idx_stride; A.c_stride = T[e].c_stride;
         for (int c = 0; c < 3; c++) A.M[c] = T[e].M[c];
         A.Qm = T[e].Qm; A.mod = allocs[e].mod_type; A.period = m.n_nonnull; A.F = T[e].F; A.tbs = allocs[e].tbs; A.a_idx = e;
         e++;

@@ -138,8 +138,10 @@ __device__ __forceinline__ void sfbc4(const float2 y[4], float2 h0, float2 h1, f
 struct FusedAlloc {
     const int *re_idx;        // [3][idx_stride]  PDSCH resource elements per subframe class (0, 5, other)
     const uint8_t *cseq;      // [10][c_stride]   scrambling bits per subframe number
+    const uint8_t *cseqP;     // [10][idx_stride] the same, the Qm bits of a resource element packed into one byte
     const int32_t *first_k;   // [3(K+4)]         rate-unmatch gather map
     const int32_t *first_kT;  // the same in the decoder's window-transposed output order + 12 tail entries (pair kernel only)
+    const uint16_t *inv_kT;   // [period] image position fed by e-bit k of the first lap (inverse of first_kT)
     int idx_stride, c_stride;
     int M[3];
     int Qm, mod, period, F, tbs, a_idx;

@@ -41,13 +41,31 @@ __device__ __noinline__ void emit_maxlog(float xr, float xi, float gain, int mod
         if (q < Qm) soft_r[q] = (int8_t)(cs_r[q] ? -bb[q] : bb[q]);
 }
 
+// The reference's 16QAM / 64QAM demapper makes hard decisions (+-127, liblte_phy.cc:9576, :9607): the soft bits of a resource element are a
+// function of Qm decision bits XOR Qm scrambling bits.  hard_bits() evaluates the very comparisons of demap_bits() (NaN behaves the same) and
+// returns bit q = 1 where demap_bits() gives -127.
+__device__ __forceinline__ uint32_t hard_bits(float xr, float xi, int mod)
+{
+    uint32_t h = (xr > 0.f ? 0u : 1u) | (xi > 0.f ? 0u : 2u);
+    const float ar = fabsf(xr), ai = fabsf(xi);
+    if (mod == LTEB200_MOD_16QAM) {
+        const float t = 0.63245553203367586640f;
+        h |= (ar < t ? 0u : 4u) | (ai < t ? 0u : 8u);
+    } else {
+        const float t2 = 0.30860669992418382490f, t4 = 0.61721339984836764980f, t6 = 0.92582009977255147470f;
+        if (ar < t4) h |= (ar > t2 ? 0u : 16u); else h |= 4u | (ar < t6 ? 0u : 16u);
+        if (ai < t4) h |= (ai > t2 ? 0u : 32u); else h |= 8u | (ai < t6 ? 0u : 32u);
+    }
+    return h;
+}
+
 constexpr int LUT_MAX = 4096;     // table of q over -max..max (127 x 16 repeats each way); beyond it the division is done per value
 
 // first_kT: gather map in OUTPUT order: [x][pos] for the three streams (pos = (k mod 16) * NT + k / 16, -1 on the padding) followed by the 12
 // tail entries d[3K + j].  q8 image per block: Ls[NP] | Lp1[NP] | Lp2[NP] | tail[16].
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_t *__restrict__ q8)
+__global__ void __launch_bounds__(THREADS, 4)
+pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int soft_bytes, int8_t *__restrict__ q8)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_red[32];
@@ -59,6 +77,10 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
     const int cls = sn == 0 ? 0 : (sn == 5 ? 1 : 2);
     const int M = A.M[cls], Qm = A.Qm, mod = A.mod, E = M * Qm;
     int8_t *soft = reinterpret_cast<int8_t *>(smem_raw);
+    // the image is assembled in shared memory (scattered byte stores) and leaves with 16-byte stores; positions nobody feeds stay 0 = q(0)
+    const int NP = 16 * NT, n_map = 3 * NP + 12, img_bytes = 3 * NP + 16;
+    int8_t *stage = soft + soft_bytes;
+    for (int p = t; p < img_bytes / 16; p += THREADS) reinterpret_cast<uint4 *>(stage)[p] = make_uint4(0, 0, 0, 0);
     const float2 *gr = fp.grid + (size_t)sf * 16 * fp.nsc, *ch = fp.ce + (size_t)sf * fp.N_ant * 14 * fp.nsc;
     const int *ix = A.re_idx + cls * A.idx_stride;
     const uint8_t *cs = A.cseq + (size_t)sn * A.c_stride;
@@ -86,7 +108,43 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
         __syncthreads();
     }
     const float s2 = maxlog ? s_s2 : 1.0f;
-    if (fp.N_ant != 1) {
+    // one port, reference demapper, 16QAM / 64QAM: decision bits XOR packed scrambling bits -> one table read gives the element's soft bytes
+    const bool hard_fast = fp.N_ant == 1 && !maxlog && (mod == LTEB200_MOD_16QAM || mod == LTEB200_MOD_64QAM);
+    __shared__ uint2 s_hard[64];
+    if (hard_fast) {
+        if (t < 64) {
+            uint32_t lo = 0, hi = 0;
+            for (int q = 0; q < 4; q++) lo |= (((t >> q) & 1) ? 0x81u : 0x7fu) << (8 * q);
+            for (int q = 4; q < 6; q++) hi |= (((t >> q) & 1) ? 0x81u : 0x7fu) << (8 * (q - 4));
+            s_hard[t] = make_uint2(lo, hi);
+        }
+        __syncthreads();
+        const uint8_t *cp = A.cseqP + (size_t)sn * A.idx_stride;
+        constexpr int RE_IT = 4;
+        for (int r0 = t; r0 < M; r0 += RE_IT * THREADS) {
+            int idx[RE_IT];
+            float2 yv[RE_IT], hv[RE_IT];
+            uint32_t cv[RE_IT];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) idx[u] = (r0 + u * THREADS < M) ? ix[r0 + u * THREADS] : ix[r0];
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) { yv[u] = gr[idx[u]]; hv[u] = ch[idx[u]]; cv[u] = (r0 + u * THREADS < M) ? cp[r0 + u * THREADS] : 0u; }
+#pragma unroll
+            for (int u = 0; u < RE_IT; u++) {
+                const int r = r0 + u * THREADS;
+                if (r < M) {
+                    float xr, xi;
+                    zf_1port(yv[u], hv[u], xr, xi);
+                    const uint2 w = s_hard[hard_bits(xr, xi, mod) ^ cv[u]];
+                    if (Qm == 4) *reinterpret_cast<uint32_t *>(soft + 4 * r) = w.x;
+                    else {
+                        uint16_t *o = reinterpret_cast<uint16_t *>(soft + 6 * r);
+                        o[0] = (uint16_t)w.x; o[1] = (uint16_t)(w.x >> 16); o[2] = (uint16_t)w.y;
+                    }
+                }
+            }
+        }
+    } else if (fp.N_ant != 1) {
         // transmit diversity: one thread per group of N_ant consecutive resource elements (M is a multiple of N_ant here, the launcher checks)
         const size_t ps = (size_t)14 * fp.nsc;
         auto pw2 = [](float2 h) { return __fadd_rn(__fmul_rn(h.x, h.x), __fmul_rn(h.y, h.y)); };
@@ -170,15 +228,42 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
         return w == NUL ? 0 : w;                       // turbo_decode zeroes the sentinels (liblte_phy.cc:10636-10642)
     };
     // ---- pass 1: max |v| over the 3 K + 12 outputs (padding entries are -1 -> 0)
-    const int NP = 16 * NT, n_map = 3 * NP + 12;
     const int *fkT = A.first_kT;
     const int n2 = E > period ? E - period : 0;        // e-bits [0, n2) are visited a second time at [period, period + n2)
+    // sums v[k .. k+3] of four consecutive e-bits of the first lap with their second-lap partners, as int16 lanes (v0 = elements 0, 1; v1 = 2, 3):
+    // bytes -> int16 by sign-replicating byte permutes, packed adds.  Needs 4 | k, 4 | period and k + 3 < min(E, period).
+    const bool vec_ok = two_visits && (period & 3) == 0;
+    const int n1v = (E < period ? E : period) & ~3;
+    auto sum4 = [&](int k, uint32_t &v0, uint32_t &v1) {
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(soft + k);
+        uint32_t b = 0;
+        if (k < n2) {
+            b = *reinterpret_cast<const uint32_t *>(soft + k + period);
+            if (k + 4 > n2) b &= (1u << (8 * (n2 - k))) - 1u;                       // the second lap ends inside this word
+        }
+        uint32_t a0, a1, b0, b1;
+        asm("prmt.b32 %0, %1, %1, 0x9180;" : "=r"(a0) : "r"(a));
+        asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(a1) : "r"(a));
+        asm("prmt.b32 %0, %1, %1, 0x9180;" : "=r"(b0) : "r"(b));
+        asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(b1) : "r"(b));
+        v0 = __vadd2(a0, b0); v1 = __vadd2(a1, b1);
+    };
     int mi = 0;
     if (two_visits) {
         // the first-lap e-bits [0, period) are in one-to-one correspondence with the outputs that receive anything, so the maximum over
         // the outputs is a maximum over e-bits: no index loads
         const int n1 = E < period ? E : period;
-        for (int k = t; k < n1; k += THREADS) mi = max(mi, abs((int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)));
+        if (vec_ok) {
+            uint32_t m2 = 0;                                                        // two int16 lanes of running max |v|
+            for (int k = 4 * t; k < n1v; k += 4 * THREADS) {
+                uint32_t v0, v1;
+                sum4(k, v0, v1);
+                m2 = __vmaxs2(m2, __vmaxs2(__vmaxs2(v0, __vsub2(0u, v0)), __vmaxs2(v1, __vsub2(0u, v1))));
+            }
+            mi = max((int)(m2 & 0xffffu), (int)(m2 >> 16));
+            for (int k = n1v + t; k < n1; k += THREADS) mi = max(mi, abs((int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)));
+        } else
+            for (int k = t; k < n1; k += THREADS) mi = max(mi, abs((int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)));
     } else {
         for (int j = t; j < n_map; j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
     }
@@ -200,6 +285,25 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int8_
     // ---- pass 2: quantised image, four consecutive output bytes per thread and round
     int8_t *img = q8 + (size_t)cb * (3 * NP + 16);
     const int4 *fk4 = reinterpret_cast<const int4 *>(fkT);
+    if (vec_ok && use_lut) {
+        // e-bit driven: four consecutive first-lap e-bits per step -> sums -> table -> the four image positions they feed (inverse gather map)
+        const int8_t *lutc = lut + maxi;
+        const uint16_t *inv = A.inv_kT;
+        const int n1 = E < period ? E : period;
+        for (int k = 4 * t; k < n1v; k += 4 * THREADS) {
+            uint32_t v0, v1;
+            sum4(k, v0, v1);
+            const uint2 iv = *reinterpret_cast<const uint2 *>(inv + k);
+            stage[iv.x & 0xffffu] = lutc[(int)(int16_t)(v0 & 0xffffu)];
+            stage[iv.x >> 16] = lutc[(int)v0 >> 16];
+            stage[iv.y & 0xffffu] = lutc[(int)(int16_t)(v1 & 0xffffu)];
+            stage[iv.y >> 16] = lutc[(int)v1 >> 16];
+        }
+        for (int k = n1v + t; k < n1; k += THREADS) stage[inv[k]] = lutc[(int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)];
+        __syncthreads();
+        for (int p = t; p < img_bytes / 16; p += THREADS) reinterpret_cast<uint4 *>(img)[p] = reinterpret_cast<const uint4 *>(stage)[p];
+        return;
+    }
     if (two_visits && use_lut) {
         const int8_t *lutc = lut + maxi;
         auto q2 = [&](int fk) -> uint32_t {
@@ -232,10 +336,11 @@ int pdsch_llr_q8_launch(lteb200_ctx *ctx, const FusedParams &fp, int K, int E_ma
 {
     constexpr int THREADS = 256;
     const int NT = mlm_size_class(K);
-    const size_t smem = ((size_t)E_max + 15) & ~(size_t)15;
+    const size_t soft_bytes = ((size_t)E_max + 15) & ~(size_t)15;
+    const size_t smem = soft_bytes + 3 * 16 * (size_t)NT + 16;
     if (smem > 200 * 1024) { lteb200_set_error(ctx, "PDSCH: %d soft bits per transport block exceed the shared-memory staging", E_max); return LTEB200_ERR_UNSUPPORTED; }
     LTE_CUDA_OK(ctx, cudaFuncSetAttribute(pdsch_llr_q8_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pdsch_llr_q8_kernel<THREADS><<<fp.n_al * fp.n_sf, THREADS, smem, stream>>>(fp, K, NT, d_q8);
+    pdsch_llr_q8_kernel<THREADS><<<fp.n_al * fp.n_sf, THREADS, smem, stream>>>(fp, K, NT, (int)soft_bytes, d_q8);
     ctx->launches += 1;
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;

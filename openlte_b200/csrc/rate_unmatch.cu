@@ -120,6 +120,11 @@ int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int
         for (int j = 0; j < 12; j++) T[(size_t)3 * NP + j] = first[3 * K + j];
         LTE_CUDA_OK(ctx, cudaMalloc(&m.first_kT, sizeof(int32_t) * T.size()));
         LTE_CUDA_OK(ctx, cudaMemcpy(m.first_kT, T.data(), sizeof(int32_t) * T.size(), cudaMemcpyHostToDevice));
+        // the inverse: image position of the output that e-bit k (first lap, k < period) feeds; every e-bit of a lap feeds exactly one output
+        std::vector<uint16_t> inv(((size_t)rank + 7) & ~(size_t)7, 0xffffu);
+        for (size_t j = 0; j < T.size(); j++) if (T[j] >= 0) inv[T[j]] = (uint16_t)j;
+        LTE_CUDA_OK(ctx, cudaMalloc(&m.inv_kT, sizeof(uint16_t) * inv.size()));
+        LTE_CUDA_OK(ctx, cudaMemcpy(m.inv_kT, inv.data(), sizeof(uint16_t) * inv.size(), cudaMemcpyHostToDevice));
     }
     ctx->rum[key] = m;
     *out = m;
