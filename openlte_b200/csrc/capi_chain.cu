@@ -245,7 +245,8 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
         // growth step exposed time.  Chunks therefore start small and grow only as fast as the compute backlog allows
         // (size <= first + 0.12 x subframes already queued keeps the decode stream from ever waiting for a copy), and every size is a
         // whole number of decoder waves (148 SMs x resident blocks / transport blocks per subframe) so that no chunk ends in a
-        // partial wave.  Measured on 4000 subframes (profiles/r2_e2e_schedule.txt): 7.3 -> about 6 ms per call.
+        // partial wave.  Measured on 4000 subframes (profiles/r2_e2e_schedule.txt): 10.8 ms in one chunk, 5.9-6.2 ms with equal or doubling chunks,
+        // 5.7 ms with this schedule.
         int K_first = 6144;
         { AllocTables t0; if (get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[0], &t0) == LTEB200_OK) K_first = t0.K; }
         const int nt_class = mlm_size_class(K_first);

@@ -8,7 +8,8 @@
 // Why its own kernel: this phase is a latency-bound gather (16 bytes per resource element from the grid and the estimate, then short
 // shared-memory walks) that wants many resident warps, while the decoder is ALU-bound with 168 registers per thread and two CTAs per SM.
 // Fused into the decoder (round 1, and the first version of the pair kernel) it left the ALU pipe idle half of the time
-// (profiles/r2_fused_vs_split.json); on its own it runs at 8+ CTAs per SM, and the decoder's input shrinks to 18 KB per block.
+// (5.77 ms fused against 4.4 ms split per 16,000 blocks when the split was made); on its own it runs at 4 CTAs per SM, and the decoder's input
+// shrinks to 18 KB per block.
 //
 // The soft bits of a block stay in shared memory as int8 (the reference's demapper emits int8, descrambling multiplies by +-1), the sums of
 // repeated bits are exact in integers, and q(v) = trunc(v * 127 / max) -- IEEE multiply and divide as in the reference -- is tabulated once per

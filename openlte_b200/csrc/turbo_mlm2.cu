@@ -184,7 +184,8 @@ __device__ __forceinline__ void dec_pass(Smem<NT> &sm, const int t, const bool a
             // The inputs of steps 0..7 and the window's start metrics are needed again only after the backward recursion over steps
             // 15..8: they wait in shared memory meanwhile, which keeps the peak register demand (64 stored forward metrics + 8 backward
             // metrics + the inputs of 8 steps) under the 168 registers that two blocks per SM allow -- the first version spilled 30
-            // registers per pass to local memory and spent a fifth of the pass waiting for them (profiles/r2_pair_kernel_ncu.json).
+            // registers per pass to local memory and spent a fifth of the pass waiting for them; now 123 registers, no spills
+            // (profiles/r2_chain_ncu_summary.json).
             scr[0 * NT2] = make_uint4(in_ls[0], in_ls[1], in_ls[2], in_ls[3]);
             scr[1 * NT2] = make_uint4(in_ls[4], in_ls[5], in_ls[6], in_ls[7]);
             scr[2 * NT2] = make_uint4(in_lp[0], in_lp[1], in_lp[2], in_lp[3]);

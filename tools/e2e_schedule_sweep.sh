@@ -1,7 +1,9 @@
-run() { python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import sys, json; d=json.loads(sys.stdin.read()); print('$1', d['e2e']['ms_per_step_all_repeats'], d['e2e']['value'])"; }
-run default
-export LTEB200_E2E_SCHEDULE=256,512,1024,1184,768; run 256,512,1024,1184,768,256
-export LTEB200_E2E_SCHEDULE=192,384,768,1024,1024,416; run 192,384,768,1024,1024,416,192
-export LTEB200_E2E_SCHEDULE=160,320,640,1280,1280,224; run 160,320,640,1280,1280,224,96
-export LTEB200_E2E_SCHEDULE=128,256,512,1024,1024,768; run 128,256,512,1024,1024,768,288
+# End-to-end time of lteb200_dl_receive_host on the bench workload for a few chunk schedules (development aid; output kept as
+# profiles/r2_e2e_schedule.txt).  LTEB200_E2E_CHUNK = equal chunks, LTEB200_E2E_SCHEDULE = explicit sizes, neither = the shipped wave-aligned ramp.
+run() { echo "== $1"; python tools/e2e_trace.py 4000 2>&1 | grep -E "e2e trace|wall ms"; }
+run "shipped schedule (wave-aligned ramp 2 -> 12 waves, small last chunk)"
+LTEB200_E2E_CHUNK=296 run "equal chunks of 296 subframes (4 waves)"
+LTEB200_E2E_CHUNK=592 run "equal chunks of 592 subframes (8 waves)"
+LTEB200_E2E_CHUNK=1036 run "equal chunks of 1036 subframes (14 waves)"
+LTEB200_E2E_SCHEDULE=128,256,512,1024,1024,768 run "round-1 style doubling 128,256,512,1024,1024,768,288"
+LTEB200_E2E_CHUNK=4000 run "one chunk (no pipelining)"
