@@ -106,7 +106,11 @@ extern "C" int lteb200_get_dl_subframe_and_ce(lteb200_ctx *ctx, const float *i_s
     ctx->launches += 1;
     const long long st = start - lo;
     const int sn = subfr_num;
+    // the uploaded window starts at sample `lo` of the caller's buffer: a fused frequency shift (lteb200_set_freq_offset) must number the samples
+    // as freq_shift() does on the whole buffer (fs.cc:696-713)
+    ctx->cfo_base += lo;
     int rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, LTEB200_IQ_F32, n, fs_idx, N_rb_dl, (int)N_id_cell, N_ant, &st, &sn, 1, d_grid, d_ce, nullptr);
+    ctx->cfo_base -= lo;
     if (rc == LTEB200_OK) {
         float *s_re = d_soa, *s_im = d_soa + 4 * 16 * 1200;
         cudaMemset(d_soa, 0, sizeof(float) * 2 * 4 * 16 * 1200);

@@ -163,9 +163,29 @@ int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int
 int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, const int *d_E, int D, const RateUnmatchMap &m, int n_cb,
                             float *d_out, cudaStream_t stream);
 
-// Per-allocation device tables, cached in the context by content.
-static std::map<std::vector<int>, AllocTables> g_alloc_tabs;
+// Per-allocation device tables, cached by content (process-wide: the tables depend on the device and the allocation only).  A scan over a
+// long capture sees many distinct DCI-derived allocations, false positives included, and each pins up to ~1 MB: the cache is bounded, and
+// when it is full the oldest quarter is dropped -- after a device synchronisation, because kernels in flight may still read those tables.
+struct CachedAlloc { AllocTables t; unsigned long long stamp; };   // stamp: last use (least recently used entries go first)
+static std::map<std::vector<int>, CachedAlloc> g_alloc_tabs;
+static unsigned long long g_alloc_clock = 0;
 static std::mutex g_alloc_mu;
+constexpr size_t ALLOC_CACHE_MAX = 1024;
+static void alloc_cache_make_room()
+{
+    if (g_alloc_tabs.size() < ALLOC_CACHE_MAX) return;
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> stamps;
+    for (auto &kv : g_alloc_tabs) stamps.push_back(kv.second.stamp);
+    std::nth_element(stamps.begin(), stamps.begin() + stamps.size() / 4, stamps.end());
+    const unsigned long long cut = stamps[stamps.size() / 4];
+    for (auto it = g_alloc_tabs.begin(); it != g_alloc_tabs.end();) {
+        if (it->second.stamp < cut) {
+            cudaFree(it->second.t.re_idx); cudaFree(it->second.t.cseq); cudaFree(it->second.t.cseqP);
+            it = g_alloc_tabs.erase(it);
+        } else ++it;
+    }
+}
 
 int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, int N_pdcch_symbs, const lteb200_alloc &al, AllocTables *out)
 {
@@ -177,7 +197,8 @@ int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
     for (int s = 0; s < 2; s++) for (int j = 0; j < al.N_prb; j++) key.push_back(al.prb[s][j]);
     std::lock_guard<std::mutex> lk(g_alloc_mu);
     auto it = g_alloc_tabs.find(key);
-    if (it != g_alloc_tabs.end()) { *out = it->second; return LTEB200_OK; }
+    if (it != g_alloc_tabs.end()) { it->second.stamp = ++g_alloc_clock; *out = it->second.t; return LTEB200_OK; }
+    alloc_cache_make_room();
     AllocTables t;
     const int Qms[4] = {1, 2, 4, 6};
     t.Qm = Qms[al.mod_type];
@@ -201,7 +222,7 @@ int get_alloc_tables(lteb200_ctx *ctx, int N_rb_dl, int N_id_cell, int N_ant, in
     LTE_CUDA_OK(ctx, cudaMemcpy(t.cseqP, csp.data(), csp.size(), cudaMemcpyHostToDevice));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.re_idx, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.cseq, cs.data(), cs.size(), cudaMemcpyHostToDevice));
-    g_alloc_tabs[key] = t;
+    g_alloc_tabs[key] = CachedAlloc{t, ++g_alloc_clock};
     *out = t;
     return LTEB200_OK;
 }

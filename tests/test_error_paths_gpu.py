@@ -46,3 +46,34 @@ def test_bad_arguments_are_refused(ctx):
     ctx.check(lib.dl_transmit_batch(ctx.h, dptr(tb), 144, C.byref(good), 1, 4, 100, 0, 1, p(sn), 1, 2, dptr(grid), None, stream_ptr()))
     torch.cuda.synchronize()
     assert float(grid.abs().sum()) > 0
+
+
+def test_allocation_table_cache_is_bounded(ctx):
+    """The per-allocation device tables (RE lists, scrambling sequences) are cached by content; a long scan meets thousands of distinct
+    DCI-derived allocations.  More distinct allocations than the cache holds: old entries are dropped, results stay right for
+    allocations met before and after the eviction."""
+    import torch
+    lib = ctx.lib
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    sn = np.array([3], np.int32)
+    rng = np.random.default_rng(5)
+    tbs = 144
+    bits = torch.from_numpy(rng.integers(0, 2, (1, 1, tbs)).astype(np.uint8)).cuda()
+    first = Alloc.make(1, [0, 1, 2, 3], tbs, 0x4000)
+    grid = torch.zeros((1, 16, 72, 2), dtype=torch.float32, device="cuda")
+    ctx.check(lib.dl_transmit_batch(ctx.h, dptr(bits), tbs, C.byref(first), 1, 0, 6, 7, 1, p(sn), 1, 2, dptr(grid), None, stream_ptr()))
+    ce = torch.zeros((1, 1, 14, 72, 2), dtype=torch.float32, device="cuda"); ce[..., 0] = 1.0
+    out = torch.zeros((1, 1, tbs), dtype=torch.uint8, device="cuda"); ok = torch.zeros((1, 1), dtype=torch.int32, device="cuda")
+
+    def decode(al):
+        ok.zero_()
+        ctx.check(lib.pdsch_decode_batch(ctx.h, dptr(grid), dptr(ce), 6, 7, 1, p(sn), 1, 2, C.byref(al), 1, 0, 8, dptr(out), tbs, dptr(ok), stream_ptr()))
+        torch.cuda.synchronize()
+        return int(ok.item()), out.cpu().numpy().copy()
+
+    ok0, tb0 = decode(first)
+    assert ok0 == 1 and np.array_equal(tb0, bits.cpu().numpy())
+    for i in range(1300):                                   # distinct RNTIs = distinct scrambling sequences = distinct cache entries
+        decode(Alloc.make(1, [0, 1, 2, 3], tbs, 0x5000 + i))
+    ok1, tb1 = decode(first)                                # evicted meanwhile and rebuilt
+    assert ok1 == 1 and np.array_equal(tb1, tb0)

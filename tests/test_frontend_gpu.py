@@ -294,6 +294,22 @@ def test_front_end_freq_shift(ctx, port):
         ctx.check(ctx.lib.set_freq_offset(ctx.h, 0.0, 0))
     assert np.array_equal(g_got, g_want), "fused shift must reproduce the two-pass result exactly (same arithmetic, same order)"
     assert np.array_equal(c_got, c_want)
+    # the host twin uploads only the subframe's window: the fused shift must still number the samples from the start of the caller's buffer
+    pp = lambda a: a.ctypes.data_as(C.c_void_p)
+    def twin(i_s, q_s):
+        rr = np.zeros((16, 1200), np.float32); ri = np.zeros((16, 1200), np.float32)
+        cr = np.zeros((4, 16, 1200), np.float32); ci = np.zeros((4, 16, 1200), np.float32)
+        i_s = np.ascontiguousarray(i_s, np.float32); q_s = np.ascontiguousarray(q_s, np.float32)
+        ctx.check(ctx.lib.get_dl_subframe_and_ce(ctx.h, pp(i_s), pp(q_s), i_s.size, fs_idx, n_rb, int(case["frame_start"]), int(case["subfr"]), cell, 1,
+                                                 pp(rr), pp(ri), pp(cr), pp(ci)))
+        return rr, ri
+    w_re, w_im = twin(gi, gq)
+    ctx.check(ctx.lib.set_freq_offset(ctx.h, f, 0))
+    try:
+        t_re, t_im = twin(case["i"], case["q"])
+    finally:
+        ctx.check(ctx.lib.set_freq_offset(ctx.h, 0.0, 0))
+    assert np.array_equal(t_re, w_re) and np.array_equal(t_im, w_im), "host twin with a fused shift: sample numbering must not restart at the uploaded window"
     # and against the oracle chain: shift then demodulate
     rx_re, rx_im, _, _ = port.get_dl_subframe_and_ce(wi, wq, fs_idx, n_rb, int(case["frame_start"]), int(case["subfr"]), cell, 1)
     want_g = (rx_re + 1j * rx_im)[:, :12 * n_rb]
