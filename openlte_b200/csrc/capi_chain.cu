@@ -30,18 +30,17 @@ extern "C" int lteb200_get_dl_subframe_and_ce_batch(lteb200_ctx *ctx, const void
 {
     if (!ctx || !d_iq || !start_idx || !subfr_num || !d_grid || !d_ce || n_sf < 1 || n_samps < 1) return LTEB200_ERR_ARGS;
     cudaStream_t stream = (cudaStream_t)stream_;
+    StreamScope scope;               // stream-ordered temporaries are released on every exit path
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) { lteb200_set_error(ctx, "subframe number out of range"); return LTEB200_ERR_ARGS; }
     long long *d_start = nullptr;
     int *d_sn = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_start, sizeof(long long) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_sn, sizeof(int) * n_sf, stream));
     if (int rc_ = lteb200_upload_small(ctx, start_idx, sizeof(long long) * n_sf, d_start, stream)) return rc_;
     if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
     if (rc == LTEB200_OK) rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
-    cudaFreeAsync(d_start, stream);
-    cudaFreeAsync(d_sn, stream);
     return rc;
 }
 
@@ -50,12 +49,12 @@ extern "C" int lteb200_ofdm_demod_batch(lteb200_ctx *ctx, const void *d_iq, int 
 {
     if (!ctx || !d_iq || !start_idx || !d_grid || n_sf < 1) return LTEB200_ERR_ARGS;
     cudaStream_t stream = (cudaStream_t)stream_;
+    StreamScope scope;               // stream-ordered temporaries are released on every exit path
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     long long *d_start = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_start, sizeof(long long) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_start, sizeof(long long) * n_sf, stream));
     if (int rc_ = lteb200_upload_small(ctx, start_idx, sizeof(long long) * n_sf, d_start, stream)) return rc_;
     int rc = ofdm_demod_launch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, d_start, n_sf, d_grid, stream);
-    cudaFreeAsync(d_start, stream);
     return rc;
 }
 
@@ -64,13 +63,13 @@ extern "C" int lteb200_chan_est_batch(lteb200_ctx *ctx, const float *d_grid, con
 {
     if (!ctx || !d_grid || !subfr_num || !d_ce || n_sf < 1 || N_rb_dl < 6 || N_rb_dl > 100) return LTEB200_ERR_ARGS;
     cudaStream_t stream = (cudaStream_t)stream_;
+    StreamScope scope;               // stream-ordered temporaries are released on every exit path
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     for (int i = 0; i < n_sf; i++) if (subfr_num[i] < 0 || subfr_num[i] > 9) return LTEB200_ERR_ARGS;
     int *d_sn = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_sn, sizeof(int) * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_sn, sizeof(int) * n_sf, stream));
     if (int rc_ = lteb200_upload_small(ctx, subfr_num, sizeof(int) * n_sf, d_sn, stream)) return rc_;
     int rc = chan_est_launch(ctx, d_grid, d_sn, N_rb_dl, N_id_cell, N_ant, n_sf, d_ce, stream);
-    cudaFreeAsync(d_sn, stream);
     return rc;
 }
 
@@ -185,18 +184,17 @@ extern "C" int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int 
 {
     if (!ctx || n_sf < 1) return LTEB200_ERR_ARGS;
     cudaStream_t stream = (cudaStream_t)stream_;
+    StreamScope scope;               // stream-ordered temporaries are released on every exit path
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     const int nsc = 12 * N_rb_dl;
     float *d_grid = nullptr, *d_ce = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)n_sf * N_ant, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_grid, sizeof(float) * 2 * 16 * nsc * (size_t)n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_ce, sizeof(float) * 2 * 14 * nsc * (size_t)n_sf * N_ant, stream));
     int rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, start_idx, subfr_num, n_sf, d_grid,
                                                   d_ce, stream);
     if (rc == LTEB200_OK)
         rc = lteb200_pdsch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, subfr_num, n_sf, N_pdcch_symbs, allocs, n_alloc, turbo_mode,
                                         n_iter, d_tb_bits, tb_stride, d_crc_ok, stream);
-    cudaFreeAsync(d_grid, stream);
-    cudaFreeAsync(d_ce, stream);
     return rc;
 }
 

@@ -274,10 +274,10 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int s
     if (t < 32) {
         int v = t < THREADS / 32 ? s_red[t] : 0;
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (t == 0) s_red[0] = v;
+        if (t == 0) s_red[31] = v;                           // (its own slot: lanes of this warp have just read s_red[0..7])
     }
     __syncthreads();
-    const int maxi = s_red[0];
+    const int maxi = s_red[31];
     const float maxv = (float)maxi;
     // q(v) tabulated over -maxi..maxi (index v + maxi)
     const bool use_lut = 2 * maxi < LUT_MAX;

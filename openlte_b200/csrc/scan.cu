@@ -31,16 +31,17 @@ extern "C" int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_
     if (!ctx || !d_iq || !start_idx || !subfr_num || !results || !tb_bits || !tb_used || n_sf < 1 || tb_capacity < 0) return LTEB200_ERR_ARGS;
     if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     cudaStream_t stream = (cudaStream_t)stream_;
+    StreamScope scope;               // stream-ordered temporaries are released on every exit path
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     *tb_used = 0;
     const int nsc = 12 * N_rb_dl;
     const size_t grid_row = (size_t)2 * 16 * nsc, ce_row = (size_t)2 * 14 * nsc * N_ant;     // floats per subframe
     float *d_grid = nullptr, *d_ce = nullptr;
     lteb200_pdcch_raw *d_raw = nullptr;
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_grid, sizeof(float) * grid_row * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ce, sizeof(float) * ce_row * n_sf, stream));
-    LTE_CUDA_OK(ctx, cudaMallocAsync(&d_raw, sizeof(lteb200_pdcch_raw) * n_sf, stream));
-    auto release = [&]() { cudaFreeAsync(d_grid, stream); cudaFreeAsync(d_ce, stream); cudaFreeAsync(d_raw, stream); };
+    LTE_CUDA_OK(ctx, scope.alloc(&d_grid, sizeof(float) * grid_row * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_ce, sizeof(float) * ce_row * n_sf, stream));
+    LTE_CUDA_OK(ctx, scope.alloc(&d_raw, sizeof(lteb200_pdcch_raw) * n_sf, stream));
+    auto release = [&]() { scope.release(d_grid, stream); scope.release(d_ce, stream); scope.release(d_raw, stream); };
     int rc = lteb200_get_dl_subframe_and_ce_batch(ctx, d_iq, iq_fmt, n_samps, fs_idx, N_rb_dl, N_id_cell, N_ant, start_idx, subfr_num, n_sf, d_grid, d_ce, stream);
     if (rc == LTEB200_OK) rc = lteb200_pdcch_decode_batch(ctx, d_grid, d_ce, N_rb_dl, N_id_cell, N_ant, phich_res, subfr_num, n_sf, d_raw, stream);
     std::vector<lteb200_pdcch_raw> raw(n_sf);
@@ -85,11 +86,11 @@ extern "C" int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_
         float *g2 = nullptr, *c2 = nullptr;
         uint8_t *d_tb = nullptr;
         int32_t *d_ok = nullptr;
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_rows, sizeof(int) * m, stream));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&g2, sizeof(float) * grid_row * m, stream));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&c2, sizeof(float) * ce_row * m, stream));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_tb, (size_t)m * tbs, stream));
-        LTE_CUDA_OK(ctx, cudaMallocAsync(&d_ok, sizeof(int32_t) * m, stream));
+        LTE_CUDA_OK(ctx, scope.alloc(&d_rows, sizeof(int) * m, stream));
+        LTE_CUDA_OK(ctx, scope.alloc(&g2, sizeof(float) * grid_row * m, stream));
+        LTE_CUDA_OK(ctx, scope.alloc(&c2, sizeof(float) * ce_row * m, stream));
+        LTE_CUDA_OK(ctx, scope.alloc(&d_tb, (size_t)m * tbs, stream));
+        LTE_CUDA_OK(ctx, scope.alloc(&d_ok, sizeof(int32_t) * m, stream));
         rc = lteb200_upload_small(ctx, rows.data(), sizeof(int) * m, d_rows, stream);
         if (rc == LTEB200_OK) {
             gather_rows_kernel<<<dim3(8, m), 256, 0, stream>>>((const float4 *)d_grid, d_rows, (int)(grid_row / 4), (float4 *)g2);
@@ -106,7 +107,7 @@ extern "C" int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_
             rc = LTEB200_OK;                              // an allocation the receive path cannot take (e.g. no resource elements left): not decoded
             std::fill(ok.begin(), ok.end(), 0);
         }
-        cudaFreeAsync(d_rows, stream); cudaFreeAsync(g2, stream); cudaFreeAsync(c2, stream); cudaFreeAsync(d_tb, stream); cudaFreeAsync(d_ok, stream);
+        scope.release(d_rows, stream); scope.release(g2, stream); scope.release(c2, stream); scope.release(d_tb, stream); scope.release(d_ok, stream);
         if (rc != LTEB200_OK) break;
         for (int i = 0; i < m; i++) {
             lteb200_scan_result &R = results[members[i].first];

@@ -373,10 +373,10 @@ turbo_mlm2_kernel(const void *__restrict__ in, int K, int n_iter, const uint16_t
         if (t < 32) {
             float v = t < (nt >> 5) ? s_red[t] : 0.f;
             for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (t == 0) s_red[0] = v;
+            if (t == 0) s_red[31] = v;                       // (its own slot: lanes of this warp have just read s_red[0..5])
         }
         __syncthreads();
-        const float maxv = s_red[0];
+        const float maxv = s_red[31];
         // ---- second pass: quantise into the window-transposed arrays, thread t writes the (2t, 2t+1) word of every row
         if (active) {
             uint16_t *Ls16 = reinterpret_cast<uint16_t *>(sm.Ls) + t, *Lp116 = reinterpret_cast<uint16_t *>(sm.Lp1) + t, *Lp216 = reinterpret_cast<uint16_t *>(sm.Lp2) + t;

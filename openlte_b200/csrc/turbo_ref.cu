@@ -511,9 +511,10 @@ int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
     bytes += Bump::pad(nK / 2) + Bump::pad(nK);                         // dec1, dec2
     bytes += 2 * Bump::pad(2 * (size_t)chunk_cap);                      // end states
     bytes += 2 * Bump::pad(sizeof(int) * 2 * (size_t)chunk_cap) + 4096;
+    // scratch from the stream-ordered pool: calls on different streams of one context get different memory (a context-wide arena would be
+    // shared by them), and with the pool's release threshold raised (ctx.cu) steady state allocates nothing
     void *arena = nullptr;
-    rc = lteb200_arena(ctx, bytes, &arena);
-    if (rc) return rc;
+    LTE_CUDA_OK(ctx, cudaMallocAsync(&arena, bytes, stream));
     if (3 * K > 48 * 1024 || 4 * K > 48 * 1024) {
         cudaFuncSetAttribute(turbo_ref_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * K);
         cudaFuncSetAttribute(turbo_ref_final, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * K);
@@ -537,6 +538,7 @@ int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
                                                             d_bits + (size_t)base * K);
         ctx->launches += 5;
     }
+    cudaFreeAsync(arena, stream);
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;
 }

@@ -291,7 +291,21 @@ def native_lib():
                 ok = need <= have
             except OSError:
                 ok = False
-        _native = (C.CDLL(so), "-O3 -march=native") if ok else (lib(), "-O3 -march=x86-64-v3")
+        v4 = os.path.join(_HERE, "_ref", "libref_oracle_v4.so")
+        have_v4 = False
+        try:
+            for ln in open("/proc/cpuinfo"):
+                if ln.startswith("flags"):
+                    have_v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= set(ln.split(":", 1)[1].split())
+                    break
+        except OSError:
+            pass
+        if ok:
+            _native = (C.CDLL(so), "-O3 -march=native")
+        elif have_v4 and os.path.exists(v4):
+            _native = (C.CDLL(v4), "-O3 -march=x86-64-v4")
+        else:
+            _native = (lib(), "-O3 -march=x86-64-v3")
         _native[0].ref_chain_pool.restype = C.c_int
     return _native
 
