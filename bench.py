@@ -166,14 +166,15 @@ def best_thread_count(i_f, q_f, start, subfr, tb, seg):
     """The reference is single-threaded code run as one struct per thread; whether SMT siblings help depends on the host.  Calibrate once
     (short run each) over {logical CPUs, physical cores} and keep the faster: the CPU arm should be the reference at its best."""
     logical = os.cpu_count() or 1
-    cands = sorted({logical, min(logical, physical_cores())}, reverse=True)
-    best = None
+    phys = min(logical, physical_cores())
+    cands = sorted({logical, phys})
+    rates = {}
     for t in cands:
-        n = max(2 * t, 16)
-        r = cpu_reference_rate(i_f, q_f, start, subfr, n, t, tb, seg)
-        if best is None or r["rate"] > best[1]:
-            best = (t, r["rate"])
-    return best[0], {str(t): None for t in cands}
+        n = min(len(start), max(6 * t, 256))         # a few subframes per thread: short samples flatter the larger thread count
+        rates[t] = max(cpu_reference_rate(i_f, q_f, start, subfr, n, t, tb, seg)["rate"] for _ in range(2))
+    # SMT siblings have to earn their place: one thread per physical core unless all hardware threads are clearly faster
+    best = logical if (logical != phys and rates[logical] > 1.05 * rates[phys]) else phys
+    return best, {str(t): round(r, 1) for t, r in rates.items()}
 
 
 def shared_config(n_sf_step):
