@@ -174,12 +174,16 @@ __device__ __forceinline__ void stockham_pass(const T *__restrict__ iq, long lon
     }
 }
 
-template <int N, typename T, bool CFO>
+// STAGE (A/B variant, LTEB200_OFDM_TMA=1; int8 input, N = 2048): the symbol's samples come in by ONE bulk copy (cp.async.bulk + mbarrier, the
+// TMA engine) into shared memory and the first pass reads them from there, instead of sixteen 2-byte global loads per thread.
+template <int N, typename T, bool CFO, bool STAGE = false>
 __global__ void __launch_bounds__(N / 16 < 32 ? 32 : N / 16)
 ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long long *__restrict__ start_idx, OfdmParams P,
                       const float2 *__restrict__ tw, float2 *__restrict__ grid)
 {
     __shared__ float2 bufA[N + N / 16], bufB[N];
+    __shared__ __align__(16) unsigned char stage[STAGE ? (int)sizeof(T) * N + 32 : 16];
+    __shared__ __align__(8) unsigned long long stage_bar;
     const int tid = threadIdx.x;
     const int sf = blockIdx.x >> 4, sym = blockIdx.x & 15;
     const int slot = sym / 7, l = sym % 7;
@@ -188,6 +192,33 @@ ofdm_demod_r16_kernel(const T *__restrict__ iq, long long n_samps, const long lo
     float2 *out = grid + ((size_t)sf * 16 + sym) * P.nsc;
     const bool act = tid < N / 16;
     const bool inb = w0 >= 0 && w0 + N <= n_samps;          // whole window inside the stream (all but the edges of a capture): no per-sample test
+    if constexpr (STAGE) {
+        // 16-byte aligned superset of the window's bytes; windows too close to the ends of the buffer take the direct path
+        const unsigned long long g0 = (unsigned long long)(iq + w0), a0 = g0 & ~15ull;
+        const unsigned off = (unsigned)(g0 - a0), bytes = (off + (unsigned)sizeof(T) * N + 15u) & ~15u;
+        const bool staged = w0 >= 16 && w0 + N + 16 <= n_samps;              // (uniform over the block)
+        if (staged) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar), dst = (unsigned)__cvta_generic_to_shared(stage);
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(a0), "r"(bytes), "r"(bar) : "memory");
+            }
+            __syncthreads();
+            unsigned done;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+            } while (!done);
+            const T *sp = reinterpret_cast<const T *>(stage + off);
+            if (act) stockham_pass<N, 16, N, T, true, false, false, false, true, false>(sp, 0, N, nullptr, bufA, tw, out, P.h, tid);
+            __syncthreads();
+            if (act) stockham_pass<N, 16, 128, T, false, false, false, true, false>(iq, w0, n_samps, bufA, bufB, tw, out, P.h, tid);
+            __syncthreads();
+            if (act) stockham_pass<N, 8, 8, T, false, true>(iq, w0, n_samps, bufB, nullptr, tw, out, P.h, tid);
+            return;
+        }
+    }
     if constexpr (N == 2048) {          // 16 x 16 x 8
         if (act) { if (inb) stockham_pass<N, 16, 2048, T, true, false, CFO, false, true, false>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); else stockham_pass<N, 16, 2048, T, true, false, CFO, false, true>(iq, w0, n_samps, nullptr, bufA, tw, out, P.h, tid, P.cfo_hz, P.cfo_fs, P.cfo_base); }
         __syncthreads();
@@ -223,7 +254,10 @@ static void launch_r16(const T *iq, long long n_samps, const long long *d_start,
 {
     const int blocks = n_sf * 16;
     switch (P.N) {
-    case 2048: { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<2048, T, true><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
+    case 2048: { if constexpr (sizeof(T) == 2) {
+                     if (P.cfo_hz == 0.f && getenv("LTEB200_OFDM_TMA")) { ofdm_demod_r16_kernel<2048, T, false, true><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); break; }
+                 }
+                 if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<2048, T, true><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
                  else ofdm_demod_r16_kernel<2048, T, false><<<blocks, 128, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
     case 1024: { if (P.cfo_hz != 0.f) ofdm_demod_r16_kernel<1024, T, true><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid);
                  else ofdm_demod_r16_kernel<1024, T, false><<<blocks, 64, 0, stream>>>(iq, n_samps, d_start, P, tw, grid); } break;
