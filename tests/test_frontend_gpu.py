@@ -370,3 +370,27 @@ def test_fused_receive_with_transmit_diversity_equals_staged(ctx, name):
     assert res[True][2] < res[False][2], "the fused path was not taken"
     assert res[True][1] == res[False][1] == 1
     assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][0], case["tb"])
+
+
+def test_ofdm_tma_staged_variant_is_bit_identical(ctx):
+    """The A/B variant of the OFDM demodulator (LTEB200_OFDM_TMA=1: the symbol's samples arrive by one bulk copy into shared memory) must give
+    the grid of the default path bit for bit, including the windows at the ends of the buffer that fall back to direct loads."""
+    import os
+    import torch
+    rng = np.random.default_rng(11)
+    n_sf = 6
+    iq = rng.integers(-100, 101, (n_sf * 30720 + 4500, 2)).astype(np.int8)
+    start = (np.arange(n_sf, dtype=np.int64) * 30720)
+    d_iq = torch.from_numpy(iq).cuda()
+    grids = []
+    for flag in (None, "1"):
+        if flag: os.environ["LTEB200_OFDM_TMA"] = flag
+        try:
+            g = torch.zeros((n_sf, 16, 1200, 2), dtype=torch.float32, device="cuda")
+            ctx.check(ctx.lib.ofdm_demod_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, start.ctypes.data_as(C.c_void_p), n_sf, dptr(g), stream_ptr()))
+            torch.cuda.synchronize()
+            grids.append(g.cpu().numpy())
+        finally:
+            os.environ.pop("LTEB200_OFDM_TMA", None)
+    assert np.abs(grids[0]).max() > 0
+    assert np.array_equal(grids[0], grids[1])
