@@ -222,6 +222,40 @@ def test_host_pointer_pipeline_equals_device_path(ctx):
         os.environ.pop("LTEB200_E2E_CHUNK", None)
 
 
+def test_host_pipeline_with_duplicate_and_gapped_start_indices(ctx):
+    """the host pipeline copies the sample stream chunk by chunk; a chunk's copy must cover everything its LAST subframe reads even when
+    start indices repeat (the same subframe listed twice) or jump (subframes skipped), otherwise the OFDM kernel races the copy of the next chunk."""
+    from openlte_b200 import synth
+    cell = 33
+    allocs = [dict(mod=3, prb=list(range(25 * a, 25 * a + 25)), tbs=6120, rnti=0x200 + a) for a in range(2)]
+    tx = synth.make_subframes(10, allocs, N_id_cell=cell, seed=21, first_subfr=3)
+    seg = tx["samples"].reshape(-1)
+    n_stream = 200
+    stream = np.concatenate([np.tile(seg, n_stream // 10), synth.crs_only_tail(100, cell, 3, 4)[:8192]])
+    sc = 100.0 / np.abs(np.concatenate([stream.real, stream.imag])).max()
+    iq = np.stack([np.rint(stream.real * sc), np.rint(stream.imag * sc)], -1).astype(np.int8)
+    # every subframe of 0..59 twice in a row, then a jump to 120..199
+    which = np.concatenate([np.repeat(np.arange(60), 2), np.arange(120, 200)])
+    n_sf = which.size
+    start = (which * 30720).astype(np.int64); sn = ((3 + which) % 10).astype(np.int32)
+    c_allocs = (Alloc * 2)(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
+    h_tb = np.full((n_sf, 2, 6120), 7, np.uint8); h_ok = np.zeros((n_sf, 2), np.int32)
+    pv = lambda a: a.ctypes.data_as(C.c_void_p)
+    os.environ["LTEB200_E2E_CHUNK"] = "64"
+    try:
+        for _ in range(3):                      # (a race would not show on every run)
+            h_tb[:] = 7; h_ok[:] = 0
+            ctx.check(ctx.lib.dl_receive_host(ctx.h, pv(iq), 1, iq.shape[0], 4, 100, cell, 1, pv(start), pv(sn), n_sf, 2, c_allocs, 2, 1, 8, pv(h_tb), 6120, pv(h_ok)))
+            assert h_ok.all()
+            for a in range(2):
+                assert np.array_equal(h_tb[:, a], tx["tb"][a][which % 10])
+    finally:
+        os.environ.pop("LTEB200_E2E_CHUNK", None)
+    # decreasing start indices are refused (stated precondition)
+    bad = start.copy(); bad[5] = bad[3] - 30720
+    assert ctx.lib.dl_receive_host(ctx.h, pv(iq), 1, iq.shape[0], 4, 100, cell, 1, pv(bad), pv(sn), n_sf, 2, c_allocs, 2, 1, 8, pv(h_tb), 6120, pv(h_ok)) == -1
+
+
 def test_wide_allocation_falls_back_to_staged_kernels(ctx):
     """An allocation whose soft bits do not fit the fused kernel's shared-memory staging area (100 PRB, 64QAM: 82,800 bits for one
     K = 6144 block) must still decode (staged kernels), and small block sizes take the small-footprint instantiation."""
