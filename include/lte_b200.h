@@ -308,6 +308,13 @@ enum { LTEB200_DEMAP_REFERENCE = 0, LTEB200_DEMAP_MAXLOG = 1 };
 enum { LTEB200_TB_BYTES = 0, LTEB200_TB_PACKED = 1 };
 int lteb200_set_tb_format(lteb200_ctx *ctx, int format);
 int lteb200_set_demapper(lteb200_ctx *ctx, int demap);
+/* Internal interleaver of the turbo code, for every entry point that encodes or decodes (turbo_decode*, pdsch_decode*, dl_receive*, dl_scan*,
+ * dl_transmit*).  REFERENCE (default): pi(i) = ((f1 i + f2 i^2) mod 2^32) mod K -- the reference computes the quadratic in uint32
+ * (liblte_phy.cc:10982), which for the larger block sizes is NOT a permutation and not what an LTE eNodeB transmits; encoder and decoder
+ * of the reference agree with each other, and this mode reproduces both bit for bit.  SPEC: pi(i) = (f1 i + f2 i^2) mod K as 3GPP TS 36.212
+ * 5.1.3.2.3 defines it -- the mode for signals that did not come from the reference's own transmitter.  No reference counterpart. */
+enum { LTEB200_QPP_REFERENCE = 0, LTEB200_QPP_SPEC = 1 };
+int lteb200_set_interleaver(lteb200_ctx *ctx, int qpp);
 
 /* --------------------------------------------------------------------------------------------- utilities */
 /* Pseudo-random sequence c(n), generate_prs_c (liblte_phy.cc:9669-9704); d_c DEVICE [len] bytes. */

@@ -55,6 +55,7 @@ struct lteb200_ctx {
     long long    cfo_base;
     int          demap;        // LTEB200_DEMAP_* for the max-log-MAP receive path
     int          tb_packed;    // LTEB200_TB_*
+    int          qpp_spec;     // LTEB200_QPP_*: interleaver of the turbo code (tables are cached per (K, this))
     // pinned, device-mapped ring for small per-call parameter arrays (see lteb200_upload_small)
     char        *ring_h, *ring_d;
     size_t       ring_bytes, ring_off;

@@ -38,6 +38,7 @@ extern "C" int lteb200_create(lteb200_ctx **out, int device)
     c->cfo_hz = 0.f; c->cfo_base = 0;
     c->demap = LTEB200_DEMAP_REFERENCE;
     c->tb_packed = LTEB200_TB_BYTES;
+    c->qpp_spec = LTEB200_QPP_REFERENCE;
     c->s_h2d = c->s_comp = c->s_d2h = c->s_front = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LTEB200_ERR_CUDA; }
     // Stage buffers come from the stream-ordered allocator; keep freed blocks in the pool across synchronisations,
@@ -74,6 +75,13 @@ extern "C" int lteb200_set_tb_format(lteb200_ctx *c, int format)
     return LTEB200_OK;
 }
 
+extern "C" int lteb200_set_interleaver(lteb200_ctx *c, int qpp)
+{
+    if (!c || (qpp != LTEB200_QPP_REFERENCE && qpp != LTEB200_QPP_SPEC)) return LTEB200_ERR_ARGS;
+    c->qpp_spec = qpp;              // (tables are cached per (K, mode): nothing to invalidate)
+    return LTEB200_OK;
+}
+
 extern "C" int lteb200_set_demapper(lteb200_ctx *c, int demap)
 {
     if (!c || (demap != LTEB200_DEMAP_REFERENCE && demap != LTEB200_DEMAP_MAXLOG)) return LTEB200_ERR_ARGS;
@@ -102,7 +110,8 @@ int lteb200_arena(lteb200_ctx *ctx, size_t bytes, void **ptr)
 
 int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out)
 {
-    auto it = ctx->qpp.find(K);
+    const int key = K | (ctx->qpp_spec << 16);
+    auto it = ctx->qpp.find(key);
     if (it != ctx->qpp.end()) { *out = it->second; return LTEB200_OK; }
     uint32_t f1 = 0, f2 = 0;
     bool found = false;
@@ -112,8 +121,8 @@ int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out)
     std::vector<uint16_t> pi(K);
     std::vector<int16_t> inv(K, -1);
     for (uint32_t i = 0; i < (uint32_t)K; i++) {
-        // uint32 wrap-around is the reference's behaviour (liblte_phy.cc:10982)
-        uint32_t idx = (uint32_t)(f1 * i + f2 * i * i) % (uint32_t)K;
+        // uint32 wrap-around is the reference's behaviour (liblte_phy.cc:10982); LTEB200_QPP_SPEC: the permutation of 36.212 5.1.3.2.3
+        uint32_t idx = ctx->qpp_spec ? (uint32_t)(((uint64_t)f1 * i + (uint64_t)f2 * i * i) % (uint64_t)K) : (uint32_t)(f1 * i + f2 * i * i) % (uint32_t)K;
         pi[i] = (uint16_t)idx;
         inv[idx] = (int16_t)i;  // increasing i: the last writer wins, as in the sequential scatter
     }
@@ -122,7 +131,7 @@ int lteb200_get_qpp(lteb200_ctx *ctx, int K, QppTables *out)
     LTE_CUDA_OK(ctx, cudaMalloc(&t.inv_last, K * sizeof(int16_t)));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.pi, pi.data(), K * sizeof(uint16_t), cudaMemcpyHostToDevice));
     LTE_CUDA_OK(ctx, cudaMemcpy(t.inv_last, inv.data(), K * sizeof(int16_t), cudaMemcpyHostToDevice));
-    ctx->qpp[K] = t;
+    ctx->qpp[key] = t;
     *out = t;
     return LTEB200_OK;
 }

@@ -504,7 +504,7 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
     const int NT = mlm_size_class(K), NP = WIN * NT;
     MlmTables mt;
     {
-        auto it = ctx->mlm.find(K);
+        auto it = ctx->mlm.find(K | (ctx->qpp_spec << 16));
         if (it == ctx->mlm.end()) {
             std::vector<uint16_t> pi(K);
             LTE_CUDA_OK(ctx, cudaMemcpy(pi.data(), qt.pi, K * sizeof(uint16_t), cudaMemcpyDeviceToHost));
@@ -526,7 +526,7 @@ static int turbo_mlm_launch(lteb200_ctx *ctx, const float *d_llr, int K, int n_c
             LTE_CUDA_OK(ctx, cudaMemcpy(mt.piT, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice));
             mt.csr_start = mt.piT + NP;
             mt.csr_pos = mt.csr_start + NP + 8;
-            ctx->mlm[K] = mt;
+            ctx->mlm[K | (ctx->qpp_spec << 16)] = mt;
         } else mt = it->second;
     }
     const size_t smem = (size_t)16 * NP + (size_t)4 * NT * 16 + (size_t)2 * NP * 2 + (size_t)(3 * NP + (fused ? 4 : 16)) * 2 + (size_t)3 * NP;

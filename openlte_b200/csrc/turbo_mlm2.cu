@@ -571,7 +571,7 @@ int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, const int8_t *q8, in
     const int NT = mlm_size_class(K), NP = WIN * NT;
     uint16_t *piT2 = nullptr;
     {
-        auto it = ctx->mlm2.find(K);
+        auto it = ctx->mlm2.find(K | (ctx->qpp_spec << 16));
         if (it == ctx->mlm2.end()) {
             std::vector<uint16_t> pi(K);
             LTE_CUDA_OK(ctx, cudaMemcpy(pi.data(), qt.pi, K * sizeof(uint16_t), cudaMemcpyDeviceToHost));
@@ -580,7 +580,7 @@ int turbo_mlm2_launch(lteb200_ctx *ctx, const float *d_llr, const int8_t *q8, in
             for (int k = 0; k < K; k++) tab[pos(k)] = (uint16_t)(2 * pos(pi[k]));
             LTE_CUDA_OK(ctx, cudaMalloc(&piT2, (size_t)NP * 2));
             LTE_CUDA_OK(ctx, cudaMemcpy(piT2, tab.data(), (size_t)NP * 2, cudaMemcpyHostToDevice));
-            ctx->mlm2[K] = piT2;
+            ctx->mlm2[K | (ctx->qpp_spec << 16)] = piT2;
         } else piT2 = it->second;
     }
     const int n_thr = K / (2 * WIN);

@@ -93,6 +93,7 @@ SYMBOLS = {
     "lteb200_dl_scan_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),
     "lteb200_set_demapper": (_i, [_vp, _i]),
     "lteb200_set_tb_format": (_i, [_vp, _i]),
+    "lteb200_set_interleaver": (_i, [_vp, _i]),
     "lteb200_q8_stride": (C.c_size_t, [_i]),
     "lteb200_pdsch_llr_q8_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_turbo_decode_q8_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),

@@ -31,6 +31,18 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def set_qpp_spec(on):
+    """Interleaver of every port function: False = the reference's uint32-wrapping one (default), True = 3GPP TS 36.212's."""
+    lib().op_set_qpp_spec(1 if on else 0)
+
+
+def qpp_params(K):
+    """(f1, f2) of 36.212 table 5.1.3-3 for block size K."""
+    f1 = C.c_uint32(0); f2 = C.c_uint32(0)
+    lib().op_qpp_params(K, C.byref(f1), C.byref(f2))
+    return int(f1.value), int(f2.value)
+
+
 def qpp_pi(K):
     out = np.zeros(K, np.uint32); lib().op_qpp_pi(K, _p(out)); return out
 

@@ -20,6 +20,7 @@ extern "C" {
 
 /* ---- turbo */
 int  op_qpp_params(int K, uint32_t *f1, uint32_t *f2);                 /* 0 if K is a legal block size */
+void op_set_qpp_spec(int on);                                        /* 1: 36.212 permutation without the uint32 wrap (library option LTEB200_QPP_SPEC) */
 void op_qpp_pi(int K, uint32_t *pi);                                   /* 32-bit-overflowing pi(i), liblte_phy.cc:10982 */
 void op_turbo_encode(const uint8_t *c, int K, uint8_t *d_branch_major);/* liblte_phy.cc:10541-10586 */
 /* d: interleaved d[3i+x], 3(K+4) floats, modified in place like the reference; out: K bytes.

@@ -23,12 +23,17 @@ extern "C" int op_qpp_params(int K, uint32_t *f1, uint32_t *f2)
     return -1;
 }
 
-/* pi(i) = ((f1*i + f2*i*i) mod 2^32) mod K  -- the uint32 wrap is the reference's behaviour */
+/* pi(i) = ((f1*i + f2*i*i) mod 2^32) mod K  -- the uint32 wrap is the reference's behaviour.
+ * op_set_qpp_spec(1) switches every function of this port that interleaves to the permutation 3GPP TS 36.212 5.1.3.2.3 defines,
+ * (f1*i + f2*i*i) mod K without the wrap: the twin of the library's LTEB200_QPP_SPEC option (no reference counterpart). */
+static int g_qpp_spec = 0;
+extern "C" void op_set_qpp_spec(int on) { g_qpp_spec = on ? 1 : 0; }
 extern "C" void op_qpp_pi(int K, uint32_t *pi)
 {
     uint32_t f1, f2;
     op_qpp_params(K, &f1, &f2);
-    for (uint32_t i = 0; i < (uint32_t)K; i++) pi[i] = (uint32_t)(f1 * i + f2 * i * i) % (uint32_t)K;
+    for (uint32_t i = 0; i < (uint32_t)K; i++)
+        pi[i] = g_qpp_spec ? (uint32_t)(((uint64_t)f1 * i + (uint64_t)f2 * i * i) % (uint64_t)K) : (uint32_t)(f1 * i + f2 * i * i) % (uint32_t)K;
 }
 
 /* One RSC constituent encoder run: feedback 1+D^2+D^3, feed-forward 1+D+D^3, then 4 termination steps in
