@@ -442,7 +442,7 @@ def main():
             dist.destroy_process_group()
         return
     # ---- timed: end to end through the host-pointer C-ABI call
-    packed = bool(args.turbo_mode)          # (the reference-exact decoder keeps one bit per byte)
+    packed = True                           # eight transport-block bits per byte on the way back to the host
     if packed:
         ctx.check(lib.set_tb_format(ctx.h, 1))
     else:

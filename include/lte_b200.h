@@ -304,7 +304,8 @@ enum { LTEB200_DEMAP_REFERENCE = 0, LTEB200_DEMAP_MAXLOG = 1 };
 /* Transport-block output format of lteb200_pdsch_decode_batch / dl_receive_batch / dl_receive_host / turbo_decode_q8_batch.  BYTES (default): one
  * bit per byte like the reference's out_bits (liblte_phy.h:906-913).  PACKED: eight bits per byte, first bit in the MSB -- an eighth of the
  * device-to-host traffic; tb_stride is then in bytes of packed data (>= tbs / 8).  PACKED needs transport blocks without filler bits (tbs + 24 a
- * turbo block size) and is refused otherwise. */
+ * turbo block size), with the max-log-MAP decoder also a block size that is a multiple of 32, and an allocation the symbol-level kernel takes
+ * whole (no ragged multi-port tail, soft bits within its shared-memory staging); it is refused otherwise. */
 enum { LTEB200_TB_BYTES = 0, LTEB200_TB_PACKED = 1 };
 int lteb200_set_tb_format(lteb200_ctx *ctx, int format);
 int lteb200_set_demapper(lteb200_ctx *ctx, int demap);

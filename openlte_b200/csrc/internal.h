@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream);
+int turbo_ref_decode_q8_batch(lteb200_ctx *ctx, const int8_t *d_q8, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream);   // images of pdsch_llr_q8_launch with max_no_tail
 int turbo_mlm_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, int n_iter, uint8_t *d_bits, cudaStream_t stream);
 
 // Per-(cell, allocation, CFI) tables of the PDSCH symbol level, shared by the receive and the transmit side (pdsch.cu)

@@ -79,7 +79,7 @@ pdsch_demod_kernel(const float2 *__restrict__ grid /*[n_sf][16][nsc]*/, const fl
 // takes a strided share of the bits, so the kernel is a few hundred cycles instead of the 6000-step dependent shift loop it used to be.
 __global__ void __launch_bounds__(128)
 crc_extract_kernel(const uint8_t *__restrict__ cb_bits, int K, int F, int tbs, int n_sf, int a_idx, int n_alloc,
-                   const uint32_t *__restrict__ crc_tab, uint8_t *__restrict__ tb_out, int tb_stride, int32_t *__restrict__ crc_ok)
+                   const uint32_t *__restrict__ crc_tab, uint8_t *__restrict__ tb_out, int tb_stride, int32_t *__restrict__ crc_ok, int packed = 0)
 {
     __shared__ uint32_t s_rem[4];
     const int sf = blockIdx.x;
@@ -87,6 +87,20 @@ crc_extract_kernel(const uint8_t *__restrict__ cb_bits, int K, int F, int tbs, i
     uint8_t *o = tb_out + ((size_t)sf * n_alloc + a_idx) * tb_stride;
     const int n = tbs + 24;
     uint32_t rem = 0;
+    if (packed) {
+        // eight bits per output byte, first bit in the MSB (the launcher admits this format only without filler bits: F = 0, n = K, 8 | K)
+        for (int b = threadIdx.x; b < n / 8; b += blockDim.x) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(a + 8 * b);
+            uint32_t byte = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t bit = ((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 1u;
+                byte |= bit << (7 - j);
+                if (bit) rem ^= crc_tab[n - 1 - (8 * b + j)];
+            }
+            if (8 * b < tbs) o[b] = (uint8_t)byte;
+        }
+    } else
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t bit = a[i] & 1u;
         if (i < tbs) o[i] = a[i];
@@ -395,8 +409,8 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
         rc = get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[a], &T[a]);
         if (rc) return rc;
         if (tb_stride < (ctx->tb_packed ? (allocs[a].tbs + 7) / 8 : allocs[a].tbs)) { lteb200_set_error(ctx, "tb_stride < tbs"); return LTEB200_ERR_ARGS; }
-        if (ctx->tb_packed && (T[a].F != 0 || !mlm2_handles(T[a].K) || turbo_mode != LTEB200_TURBO_MAXLOGMAP)) {
-            lteb200_set_error(ctx, "packed transport-block output: max-log-MAP path, block sizes that are multiples of 32, no filler bits (tbs + 24 = K)");
+        if (ctx->tb_packed && (T[a].F != 0 || (turbo_mode == LTEB200_TURBO_MAXLOGMAP && !mlm2_handles(T[a].K)))) {
+            lteb200_set_error(ctx, "packed transport-block output: no filler bits (tbs + 24 = K), and block sizes that are multiples of 32 with the max-log-MAP decoder");
             return LTEB200_ERR_UNSUPPORTED;
         }
     }
@@ -444,6 +458,56 @@ int pdsch_decode_batch_dev(lteb200_ctx *ctx, const float *d_grid, const float *d
         if (!d_subfr_dev) cudaFreeAsync(d_sn, stream);
         return rc;
     }
+    // ---- reference-exact decoder on quantised images: the symbol-level kernel of the max-log-MAP path (reference demapper, quantisation maximum
+    // over the 3 K code-block values like turbo_decode's own) feeds turbo_ref's front end directly -- no float soft bits, no separate rate-unmatch
+    // pass.  Bit-identical to the staged kernels below, which remain for allocations that do not fit (and for LTEB200_NO_FUSE=1).
+    bool q8_ref = turbo_mode == LTEB200_TURBO_REF_EXACT && !getenv("LTEB200_NO_FUSE");
+    for (int a = 0; a < n_alloc && q8_ref; a++) {
+        for (int c = 0; c < 3; c++) if (T[a].M[c] % N_ant != 0) q8_ref = false;
+        if ((size_t)T[a].M[2] * T[a].Qm + mlm2_q8_stride(T[a].K) > 190 * 1024) q8_ref = false;
+    }
+    if (q8_ref) {
+        int *d_sn = const_cast<int *>(d_subfr_dev);
+        if (!d_sn) {
+            rc = upload_ints(ctx, subfr_num, n_sf, &d_sn, stream);
+            if (rc) return rc;
+        }
+        const uint32_t *crc_tab = nullptr;
+        rc = lteb200_get_crc24a_tab(ctx, &crc_tab);
+        for (int a = 0; a < n_alloc && rc == LTEB200_OK;) {
+            FusedParams fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.grid = (const float2 *)d_grid; fp.ce = (const float2 *)d_ce; fp.subfr_num = d_sn; fp.crc_tab = crc_tab;
+            fp.N_ant = N_ant;
+            fp.demap = LTEB200_DEMAP_REFERENCE; fp.vshift = N_id_cell % 6; fp.tb_packed = 0; fp.max_no_tail = 1;
+            fp.tb_out = d_tb_bits; fp.crc_ok = d_crc_ok; fp.nsc = 12 * N_rb_dl; fp.n_sf = n_sf; fp.n_alloc_total = n_alloc; fp.tb_stride = tb_stride;
+            int e = a;
+            rc = fill_group(ctx, T, allocs, n_alloc, a, &e, fp);
+            if (rc) break;
+            const int K = T[a].K;
+            int E_max = 0;
+            for (int q = a; q < e; q++) E_max = std::max(E_max, T[q].M[2] * T[q].Qm);
+            int8_t *d_q8 = nullptr;
+            uint8_t *d_cb = nullptr;
+            LTE_CUDA_OK(ctx, cudaMallocAsync(&d_q8, mlm2_q8_stride(K) * (size_t)fp.n_al * n_sf, stream));
+            LTE_CUDA_OK(ctx, cudaMallocAsync(&d_cb, (size_t)K * fp.n_al * n_sf, stream));
+            rc = pdsch_llr_q8_launch(ctx, fp, K, E_max, d_q8, stream);
+            if (rc == LTEB200_OK) rc = turbo_ref_decode_q8_batch(ctx, d_q8, K, fp.n_al * n_sf, d_cb, stream);
+            for (int q = a; q < e && rc == LTEB200_OK; q++) {
+                crc_extract_kernel<<<n_sf, 128, 0, stream>>>(d_cb + (size_t)(q - a) * n_sf * K, K, T[q].F, allocs[q].tbs, n_sf, q, n_alloc, crc_tab, d_tb_bits, tb_stride, d_crc_ok,
+                                                             ctx->tb_packed);
+                ctx->launches += 1;
+            }
+            cudaFreeAsync(d_q8, stream);
+            cudaFreeAsync(d_cb, stream);
+            a = e;
+        }
+        if (!d_subfr_dev) cudaFreeAsync(d_sn, stream);
+        if (rc) return rc;
+        LTE_CUDA_OK(ctx, cudaGetLastError());
+        return LTEB200_OK;
+    }
+    if (ctx->tb_packed) { lteb200_set_error(ctx, "packed transport-block output is not available on the staged path (allocation too wide for the symbol-level kernel, ragged multi-port tail, or LTEB200_NO_FUSE)"); return LTEB200_ERR_UNSUPPORTED; }
     // per-call device parameter arrays: subframe numbers and per-(alloc, subframe) E
     std::vector<int> hpar((size_t)n_sf * (1 + n_alloc));
     for (int i = 0; i < n_sf; i++) hpar[i] = subfr_num[i];

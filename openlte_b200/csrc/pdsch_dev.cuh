@@ -156,6 +156,7 @@ struct FusedParams {
     int N_ant;                // 1: zero forcing; 2 / 4: transmit-diversity combining of groups of N_ant resource elements
     int demap;                // LTEB200_DEMAP_*
     int tb_packed;            // transport-block output: 0 one bit per byte, 1 eight bits per byte (MSB first)
+    int max_no_tail;          // quantisation maximum over the 3 K code-block values only (the reference's turbo_decode, liblte_phy.cc:10645-10660)
     int vshift;               // N_id_cell mod 6: offset of the port-0 pilot tones in symbol 0 (noise estimate of the soft path)
     FusedAlloc al[8];
 };

@@ -249,6 +249,19 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int s
         asm("prmt.b32 %0, %1, %1, 0xb3a2;" : "=r"(b1) : "r"(b));
         v0 = __vadd2(a0, b0); v1 = __vadd2(a1, b1);
     };
+    // The reference-exact decoder quantises against the maximum over the 3 K code-block values and never looks at the 12 tail values
+    // (liblte_phy.cc:10645-10664): for it the e-bits that feed the tail outputs are cleared (twelve threads, one tail output each), so the
+    // maximum is the reference's and the image's tail bytes are 0.
+    if (fp.max_no_tail && two_visits) {
+        if (t < 12) {
+            const int tail_k = fkT[3 * NP + t];
+            if (tail_k >= 0) {
+                if (tail_k < E) soft[tail_k] = 0;
+                if (tail_k + period < E) soft[tail_k + period] = 0;
+            }
+        }
+        __syncthreads();
+    }
     int mi = 0;
     if (two_visits) {
         // the first-lap e-bits [0, period) are in one-to-one correspondence with the outputs that receive anything, so the maximum over
@@ -266,7 +279,7 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int s
         } else
             for (int k = t; k < n1; k += THREADS) mi = max(mi, abs((int)soft[k] + (k < n2 ? (int)soft[k + period] : 0)));
     } else {
-        for (int j = t; j < n_map; j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
+        for (int j = t; j < (fp.max_no_tail ? 3 * NP : n_map); j += THREADS) mi = max(mi, abs(unmatch(fkT[j])));
     }
     for (int o = 16; o > 0; o >>= 1) mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
     if ((t & 31) == 0) s_red[t >> 5] = mi;
@@ -315,7 +328,7 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int s
             const int4 f = fk4[j];
             reinterpret_cast<uint32_t *>(img)[j] = q2(f.x) | (q2(f.y) << 8) | (q2(f.z) << 16) | (q2(f.w) << 24);
         }
-        if (t < 16) img[3 * NP + t] = t < 12 ? (int8_t)q2(fkT[3 * NP + t]) : (int8_t)0;
+        if (t < 16) img[3 * NP + t] = (t < 12 && !fp.max_no_tail) ? (int8_t)q2(fkT[3 * NP + t]) : (int8_t)0;
         return;
     }
     auto q_int = [&](int v) -> uint32_t {
@@ -327,7 +340,7 @@ pdsch_llr_q8_kernel(const __grid_constant__ FusedParams fp, int K, int NT, int s
         const uint32_t w = q_int(unmatch(f.x)) | (q_int(unmatch(f.y)) << 8) | (q_int(unmatch(f.z)) << 16) | (q_int(unmatch(f.w)) << 24);
         reinterpret_cast<uint32_t *>(img)[j] = w;
     }
-    if (t < 16) img[3 * NP + t] = t < 12 ? (int8_t)q_int(unmatch(fkT[3 * NP + t])) : (int8_t)0;
+    if (t < 16) img[3 * NP + t] = (t < 12 && !fp.max_no_tail) ? (int8_t)q_int(unmatch(fkT[3 * NP + t])) : (int8_t)0;
 }
 
 }  // namespace

@@ -30,7 +30,7 @@
 //   * the three SISO passes run as two launches (pass 1: n_cb trellises; passes 2 and 3 are independent of
 //     each other and run together as 2*n_cb trellises).
 // No tensor cores: there is no dense contraction anywhere on this path.
-#include "common.cuh"
+#include "internal.h"
 
 namespace {
 
@@ -164,6 +164,45 @@ turbo_ref_prep(const float *__restrict__ llr, int K, int n_cb, int8_t *__restric
             if (v1 == LTEB200_RX_NULL_BIT) v1 = 0.f;
             if (v2 == LTEB200_RX_NULL_BIT) v2 = 0.f;
             const int a0 = q8(v0, maxv), a1 = q8(v1, maxv), a2 = q8(v2, maxv);
+            wm = max(wm, iabs(a1) + iabs(a0));
+            p0[s >> 2] |= (uint32_t)(a0 & 0xff) << (8 * (s & 3));
+            p1[s >> 2] |= (uint32_t)(a1 & 0xff) << (8 * (s & 3));
+            p2[s >> 2] |= (uint32_t)(a2 & 0xff) << (8 * (s & 3));
+            ds[s] = make_desc(a1, a0);
+        }
+        const size_t plane = (size_t)n_cb * K;
+        *(uint2 *)(q + 0 * plane + (size_t)cb * K + 8 * c) = make_uint2(p0[0], p0[1]);
+        *(uint2 *)(q + 1 * plane + (size_t)cb * K + 8 * c) = make_uint2(p1[0], p1[1]);
+        *(uint2 *)(q + 2 * plane + (size_t)cb * K + 8 * c) = make_uint2(p2[0], p2[1]);
+#pragma unroll
+        for (int h = 0; h < 4; h++) tile1[(size_t)(4 * c + h) * n_cb + cb] = make_uint4(ds[2 * h].x, ds[2 * h].y, ds[2 * h + 1].x, ds[2 * h + 1].y);
+    }
+    wm = block_max(wm, sh);
+    if (threadIdx.x == 0) wmax1[cb] = wm;
+}
+
+// The same front end fed by the quantised image of the symbol-level kernel (pdsch_llr.cu, written with max_no_tail = 1: quantised against
+// the maximum over the 3 K code-block values, exactly the reference's (int8)(d*127/max_value)): no float LLRs, no separate rate-unmatch pass.
+// img: [n_cb][3 NP + 16] int8, planes Ls | Lp1 | Lp2 of NP = 16 NT bytes, step k at (k mod 16) NT + k / 16.  Dynamic smem = 3 NP + 16 bytes.
+__global__ void __launch_bounds__(PREP_THREADS)
+turbo_ref_prep_q8(const int8_t *__restrict__ img, int K, int NT, int n_cb, int8_t *__restrict__ q /*[3][n_cb][K]*/,
+                  uint4 *__restrict__ tile1 /*[K/2][n_cb]*/, int *__restrict__ wmax1 /*[n_cb]*/)
+{
+    extern __shared__ __align__(16) int8_t s_img[];
+    __shared__ int sh[32];
+    const int cb = blockIdx.x, NP = 16 * NT, bytes = 3 * NP + 16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(img + (size_t)cb * bytes);
+    for (int p = threadIdx.x; p < bytes / 16; p += PREP_THREADS) reinterpret_cast<uint4 *>(s_img)[p] = src[p];
+    __syncthreads();
+    int wm = 0;
+    const int K8 = K >> 3;
+    for (int c = threadIdx.x; c < K8; c += PREP_THREADS) {
+        uint2 ds[8];
+        uint32_t p0[2] = {0, 0}, p1[2] = {0, 0}, p2[2] = {0, 0};
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const int i = 8 * c + s, pos = (i & 15) * NT + (i >> 4);
+            const int a0 = s_img[pos], a1 = s_img[NP + pos], a2 = s_img[2 * NP + pos];
             wm = max(wm, iabs(a1) + iabs(a0));
             p0[s >> 2] |= (uint32_t)(a0 & 0xff) << (8 * (s & 3));
             p1[s >> 2] |= (uint32_t)(a1 & 0xff) << (8 * (s & 3));
@@ -495,7 +534,8 @@ turbo_ref_final(const int8_t *__restrict__ q, const uint32_t *__restrict__ dec2,
 }  // namespace
 
 // Host launcher.  Splits very large batches so the scratch arena stays bounded.
-int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream)
+// d_llr: float LLRs [n_cb][3 (K + 4)], or null with d_q8: quantised images [n_cb][mlm2_q8_stride(K)] (see turbo_ref_prep_q8)
+int turbo_ref_decode_any(lteb200_ctx *ctx, const float *d_llr, const int8_t *d_q8, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream)
 {
     if (K < 40 || (K & 7)) { lteb200_set_error(ctx, "turbo: illegal K=%d", K); return LTEB200_ERR_ARGS; }
     QppTables qt;
@@ -529,8 +569,14 @@ int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
         uint32_t *dec1 = (uint32_t *)b.take<int8_t>(nK / 2), *dec2 = (uint32_t *)b.take<int8_t>(nK);
         uint8_t *end1 = b.take<uint8_t>(chunk_cap), *end2 = b.take<uint8_t>(2 * (size_t)chunk_cap);
         int *wmax1 = b.take<int>(chunk_cap), *wmax2 = b.take<int>(2 * (size_t)chunk_cap);
-        const float *llr = d_llr + (size_t)base * 3 * (K + 4);
-        turbo_ref_prep<<<n, PREP_THREADS, 0, stream>>>(llr, K, n, q, tile1, wmax1);
+        if (d_q8) {
+            const int NT = mlm_size_class(K);
+            const size_t img_bytes = 3 * 16 * (size_t)NT + 16;
+            turbo_ref_prep_q8<<<n, PREP_THREADS, img_bytes, stream>>>(d_q8 + (size_t)base * img_bytes, K, NT, n, q, tile1, wmax1);
+        } else {
+            const float *llr = d_llr + (size_t)base * 3 * (K + 4);
+            turbo_ref_prep<<<n, PREP_THREADS, 0, stream>>>(llr, K, n, q, tile1, wmax1);
+        }
         turbo_ref_siso<<<ceil_div(n, 32), 32, 0, stream>>>(tile1, K8, n, dec1, end1);
         turbo_ref_mid<<<n, PREP_THREADS, 3 * K, stream>>>(q, dec1, end1, wmax1, qt.pi, K, n, act1, calc1, sysI, c1I, tile2, wmax2);
         turbo_ref_siso<<<ceil_div(2 * n, 32), 32, 0, stream>>>(tile2, K8, 2 * n, dec2, end2);
@@ -541,4 +587,13 @@ int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb
     cudaFreeAsync(arena, stream);
     LTE_CUDA_OK(ctx, cudaGetLastError());
     return LTEB200_OK;
+}
+
+int turbo_ref_decode_batch(lteb200_ctx *ctx, const float *d_llr, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream)
+{
+    return turbo_ref_decode_any(ctx, d_llr, nullptr, K, n_cb, d_bits, stream);
+}
+int turbo_ref_decode_q8_batch(lteb200_ctx *ctx, const int8_t *d_q8, int K, int n_cb, uint8_t *d_bits, cudaStream_t stream)
+{
+    return turbo_ref_decode_any(ctx, nullptr, d_q8, K, n_cb, d_bits, stream);
 }

@@ -47,8 +47,18 @@ def test_packed_equals_packbits_of_bytes(ctx, lib):
         for a, al in enumerate(allocs):          # (bytes past a transport block's end are not written)
             assert np.array_equal(h_tb.numpy()[:, a, : al["tbs"] // 8], got[:, a, : al["tbs"] // 8]), f"host pipeline, allocation {a}"
         assert np.array_equal(h_ok.numpy(), okw)
-        # refused: reference-exact decoder, and a block size with filler bits / not a multiple of 32
-        assert lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), 4, cfi, ca, 3, 0, 8, dptr(tbp), 768, dptr(ok2), stream_ptr()) == -4
+        # the reference-exact decoder packs as well (same symbol-level kernel, its own decoder): equal to the bytes it produces unpacked
+        lib.set_tb_format(ctx.h, 0)
+        tba = torch.zeros((n_sf, 3, 6120), dtype=torch.uint8, device="cuda"); oka = torch.zeros((n_sf, 3), dtype=torch.int32, device="cuda")
+        ctx.check(lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), n_sf, cfi, ca, 3, 0, 8, dptr(tba), 6120, dptr(oka), stream_ptr()))
+        ctx.check(lib.set_tb_format(ctx.h, 1))
+        ctx.check(lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), n_sf, cfi, ca, 3, 0, 8, dptr(tbp), 768, dptr(ok2), stream_ptr()))
+        torch.cuda.synchronize()
+        wa = tba.cpu().numpy(); ga = tbp.cpu().numpy()
+        assert np.array_equal(ok2.cpu().numpy(), oka.cpu().numpy())
+        for a, al in enumerate(allocs):
+            assert np.array_equal(ga[:, a, : al["tbs"] // 8], np.packbits(wa[:, a, : al["tbs"]], axis=-1)), f"reference-exact decoder, allocation {a}"
+        # refused: a block size that is not a multiple of 32 with the max-log-MAP decoder
         odd = (Alloc * 1)(Alloc.make(1, list(range(0, 10)), 464, 0x9))          # K = 488: not a multiple of 32
         assert lib.dl_receive_batch(ctx.h, dptr(d_iq), 1, iq.shape[0], 4, 100, cell, 1, p(start), p(sn), 4, cfi, odd, 1, 1, 8, dptr(tbp), 768, dptr(ok2), stream_ptr()) == -4
     finally:
