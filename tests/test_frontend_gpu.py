@@ -176,23 +176,30 @@ def test_fused_receive_equals_staged_pipeline(ctx):
     d_iq = torch.from_numpy(iq).cuda()
     start = (np.arange(n_sf) * 30720).astype(np.int64); sn = tx["subfr_nums"].astype(np.int32)
     c_allocs = (Alloc * len(allocs))(*[Alloc.make(a["mod"], a["prb"], a["tbs"], a["rnti"]) for a in allocs])
-    res = {}
-    for fuse in (True, False):
-        if fuse:
-            os.environ.pop("LTEB200_NO_FUSE", None)
-        else:
-            os.environ["LTEB200_NO_FUSE"] = "1"
-        tb = torch.full((n_sf, len(allocs), 6120), 9, dtype=torch.uint8, device="cuda")
-        ok = torch.zeros((n_sf, len(allocs)), dtype=torch.int32, device="cuda")
-        ctx.check(ctx.lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, start.ctypes.data_as(C.c_void_p),
-                                           sn.ctypes.data_as(C.c_void_p), n_sf, 2, c_allocs, len(allocs), 1, 8, dptr(tb), 6120, dptr(ok), stream_ptr()))
-        torch.cuda.synchronize()
-        res[fuse] = (tb.cpu().numpy(), ok.cpu().numpy())
-    os.environ.pop("LTEB200_NO_FUSE", None)
-    assert np.array_equal(res[True][1], res[False][1]) and res[True][1].all()
-    for a, al in enumerate(allocs):
-        assert np.array_equal(res[True][0][:, a, :al["tbs"]], res[False][0][:, a, :al["tbs"]])
-        assert np.array_equal(res[True][0][:, a, :al["tbs"]], tx["tb"][a])
+    # turbo mode 1: max-log-MAP (symbol-level kernel + pair-lane decoder vs staged float kernels + standalone decoder);
+    # turbo mode 0: reference-exact decoder (symbol-level kernel's images vs staged float kernels): CRC verdicts may be 0 where the reference's
+    # decoder fails, but both routes must fail and succeed on the same blocks with the same bits
+    for mode in (0, 1):                     # (the max-log-MAP results are checked against the transmitted bits below)
+        res = {}
+        for fuse in (True, False):
+            if fuse:
+                os.environ.pop("LTEB200_NO_FUSE", None)
+            else:
+                os.environ["LTEB200_NO_FUSE"] = "1"
+            try:
+                tb = torch.full((n_sf, len(allocs), 6120), 9, dtype=torch.uint8, device="cuda")
+                ok = torch.zeros((n_sf, len(allocs)), dtype=torch.int32, device="cuda")
+                ctx.check(ctx.lib.dl_receive_batch(ctx.h, dptr(d_iq), 0, iq.shape[0], 4, 100, cell, 1, start.ctypes.data_as(C.c_void_p),
+                                                   sn.ctypes.data_as(C.c_void_p), n_sf, 2, c_allocs, len(allocs), mode, 8, dptr(tb), 6120, dptr(ok), stream_ptr()))
+                torch.cuda.synchronize()
+                res[fuse] = (tb.cpu().numpy(), ok.cpu().numpy())
+            finally:
+                os.environ.pop("LTEB200_NO_FUSE", None)
+        assert np.array_equal(res[True][1], res[False][1]) and (mode == 0 or res[True][1].all())
+        for a, al in enumerate(allocs):
+            assert np.array_equal(res[True][0][:, a, :al["tbs"]], res[False][0][:, a, :al["tbs"]]), f"decoder {mode}, allocation {a}"
+            if mode == 1:
+                assert np.array_equal(res[True][0][:, a, :al["tbs"]], tx["tb"][a])
 
 
 def test_host_pointer_pipeline_equals_device_path(ctx):
