@@ -107,7 +107,7 @@ class ClockSampler:
 def cpu_reference_rate(iq_f32_i, iq_f32_q, start, subfr, n_sample, threads, tb_seg, seg=SEG):
     """Times the reference's own CPU implementation of the same chain on `n_sample` subframes over `threads` host threads, one
     LIBLTE_PHY_STRUCT per thread.  With oracle/_ref present this is a native std::thread pool inside the oracle library
-    (oracle/ref_wrap.cc: ref_chain_pool -- structs and FFT plans created serially before the clock starts, no allocation per transport
+    (oracle/ref_wrap.cc: ref_chain_pool -- structs and FFT plans created serially and one untimed warm-up subframe per thread before the clock starts, no allocation per transport
     block); without it, the oracle port driven from Python threads.  Returns dict(rate, kind, note, wall_s, front_s, pdsch_s, build)."""
     from oracle import ref as refo, port
     n_tb = n_sample * len(ALLOCS)
