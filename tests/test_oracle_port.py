@@ -124,6 +124,30 @@ def test_port_against_live_reference(port, refo):
             assert np.array_equal(port.rate_unmatch_turbo(e, D, rv=rv), phy.rate_unmatch_turbo(e, D, rv=rv))
 
 
+def test_port_against_live_reference_every_block_size(port, refo):
+    """All 188 block sizes of 36.212 table 5.1.3-3, one noisy code word each (noise level cycling through clean, waterfall and
+    hopeless, sentinels on every third size): encoder, decoder (liblte_phy.cc:10541-10586, 10620-10845) and rate (un)matching
+    (:11081-11490) of the port equal the live reference.  The GPU tests compare the kernels with the port for the same 188 sizes,
+    so this closes the chain kernel == port == reference for every size, the 20 wrapped interleavers included."""
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    import re
+    rows = re.findall(r"\{\s*(\d+),\s*(\d+),\s*(\d+)\}", open(os.path.join(os.path.dirname(GOLD), "..", "openlte_b200", "csrc", "qpp_table.h")).read())
+    Ks = [int(a) for a, _, _ in rows]
+    assert len(Ks) == 188
+    phy = refo.RefPhy()
+    rng = np.random.default_rng(188)
+    for n, K in enumerate(Ks):
+        sigma = (0.0, 0.45, 0.7, 1.2)[n % 4]
+        c, x = noisy_codeword(port, K, sigma, rng, sentinel_every=11 if n % 3 == 0 else 0)
+        assert np.array_equal(port.turbo_encode(c), phy.turbo_encode(c)), K
+        assert np.array_equal(port.turbo_decode_ref(x), phy.turbo_decode(x)), K
+        D = K + 4
+        rv = n % 4
+        e = (rng.standard_normal(2 * D + 3 * (n % 50) + 9) * 2).astype(np.float32)      # punctured (E < 3D) for every size
+        assert np.array_equal(port.rate_unmatch_turbo(e, D, rv=rv), phy.rate_unmatch_turbo(e, D, rv=rv)), (K, rv)
+
+
 @pytest.mark.parametrize("name", ["loop_2ant_16qam_c21_sf2.npz", "loop_4ant_qpsk_10mhz_c400_sf5.npz", "loop_2ant_64qam_c5_sf7.npz"])
 def test_transmit_diversity_against_reference_fixtures(port, name):
     """2 / 4 antenna ports: SFBC combining + layer demapping + decode, from the reference's own grid."""
@@ -152,3 +176,54 @@ def test_freq_shift_restatement(port):
     assert np.allclose(np.abs(got), np.abs(i0[k] + 1j * q0[k]), rtol=1e-5, atol=1e-6)
     i2, q2 = port.freq_shift(i1, q1, 100, n - 300, -f, fs)
     assert np.abs(i2 - i0).max() < 1e-5 and np.abs(q2 - q0).max() < 1e-5
+
+
+def test_front_end_and_pdsch_against_live_reference_random_configs(port, refo):
+    """Randomised differential test against the reference itself (not fixtures): bandwidth, antenna ports, cell identity, subframe
+    number, CFI, modulation, PRB set, transport-block size, RNTI, channel gain and noise are drawn afresh; the signal comes from the
+    reference's own transmit functions.  Grid within the DFT tolerance (liblte_phy.cc:8593-8644); channel estimate (:5905-6200) and
+    the PDSCH receive verdict + bits (:3690-3853) of the port, from the reference's grid, equal the reference's bit for bit --
+    whether or not the block decodes."""
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    from util import ref_loopback
+    rng = np.random.default_rng(2026)
+    bands = [(30.72, 100, 4), (30.72, 75, 4), (15.36, 50, 3), (7.68, 25, 2), (3.84, 15, 1), (1.92, 6, 0)]
+    seen_fail = seen_ok = 0
+    for trial in range(42):
+        fs, n_rb, fs_idx = bands[trial % len(bands)]
+        n_ant = (1, 2, 4, 1, 1, 2, 1)[trial % 7]
+        cell = int(rng.integers(0, 504)); subfr = int(rng.integers(0, 10)); cfi = int(rng.integers(1, 4)) if n_rb > 10 else int(rng.integers(2, 4))
+        mod = int(rng.integers(1, 4))                                  # 1 QPSK, 2 16QAM, 3 64QAM
+        n_prb = int(rng.integers(1, min(n_rb, 24) + 1))
+        prb = np.sort(rng.choice(n_rb, n_prb, replace=False)).astype(np.int32)
+        # code rate between 0.05 and 0.4 of the allocation's capacity (some trials will not decode: the verdicts must still agree)
+        cap = n_prb * 120 * (2, 4, 6)[mod - 1]
+        tbs = int(max(16, min(6120, int(cap * rng.uniform(0.05, 0.4)) // 8 * 8)))
+        rnti = int(rng.integers(1, 65535))
+        noise = float(rng.choice([0.0, 0.02, 0.08]))
+        gain = complex(rng.uniform(0.5, 1.5) * np.exp(1j * rng.uniform(-np.pi, np.pi)))
+        frame_start = int(rng.integers(0, 500))
+        s = ref_loopback(refo, subfr, [dict(mod=mod, prb=prb, tbs=tbs, rnti=rnti)], N_id_cell=cell, cfi=cfi, N_rb_dl=n_rb, fs=fs, seed=trial,
+                         gain=gain, noise=noise, frame_start=frame_start, N_ant=n_ant)
+        phy = s["phy"]
+        sf = refo.Subframe(); sf.clear()
+        phy.get_dl_subframe_and_ce(s["i"], s["q"], frame_start, subfr, cell, n_ant, sf)
+        rx_re, rx_im, ce_re, ce_im = port.get_dl_subframe_and_ce(s["i"], s["q"], fs_idx, n_rb, frame_start, subfr, cell, n_ant)
+        tag = (trial, fs, n_rb, n_ant, cell, subfr, cfi, mod, n_prb, tbs)
+        # the DFT is the one tolerance-held stage (port: double precision, reference: single): 2e-6 of the grid maximum ...
+        g_re, g_im = sf.rx_symb_re.copy(), sf.rx_symb_im.copy()
+        sc = max(np.abs(g_re).max(), np.abs(g_im).max())
+        assert np.abs(rx_re - g_re).max() <= 2e-6 * sc and np.abs(rx_im - g_im).max() <= 2e-6 * sc, tag
+        # ... everything after it is exact when it starts from the reference's own grid
+        ce_re, ce_im = port.chan_est(g_re, g_im, n_rb, subfr, cell, n_ant)
+        assert np.array_equal(ce_re[:n_ant, :14], sf.rx_ce_re[:n_ant, :14]) and np.array_equal(ce_im[:n_ant, :14], sf.rx_ce_im[:n_ant, :14]), tag
+        err_ref, bits_ref = phy.pdsch_decode(sf, cfi, cell, n_ant, mod, prb, tbs, rnti)
+        rc, bits, _ = port.pdsch_decode_nant(g_re, g_im, ce_re, ce_im, n_rb, cell, n_ant, subfr, cfi, mod, prb, tbs, rnti)
+        assert (rc == 0) == (err_ref == 0), tag
+        if rc == 0:
+            assert np.array_equal(bits, bits_ref), tag
+            seen_ok += 1
+        else:
+            seen_fail += 1
+    assert seen_ok >= 15 and seen_fail >= 3, (seen_ok, seen_fail)          # the draw exercises both the decoding branch and DECODE_FAIL
