@@ -132,3 +132,59 @@ def test_product_dci_unpack_against_reference_fixtures():
             assert n.value == 1 and np.array_equal(alloc_row(allocs[0].as_dict()), row[36:]), (N, fmt)
             n_ok += 1
     assert n_ok > 100
+
+
+def test_control_channels_against_live_reference_random_configs(port, refo):
+    """Randomised differential test against the reference itself (fresh draws, not the committed fixtures): PBCH with 1/2/4 ports at every
+    bandwidth (liblte_phy.cc:3968-4100) and PCFICH + PDCCH blind decode with one to three DCI 1A messages (:4519-5134), the signal built by
+    the reference's own transmit functions, grid and estimate by its front end.  Error code, port count, MIB bits, SFN offset, CFI,
+    symbol count and every decoded allocation field of the port equal the reference's -- also where the reference fails."""
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    import sys
+    from util import ref_loopback
+    FS = {100: 30.72, 75: 30.72, 50: 15.36, 25: 7.68, 15: 3.84, 6: 1.92}
+    rng = np.random.default_rng(4242)
+    bands = (100, 75, 50, 25, 15, 6)
+    n_mib = 0
+    for t in range(30):
+        nrb = bands[t % 6]; cell = int(rng.integers(0, 504)); nant = (1, 2, 4)[(t // 6 + t) % 3]; sfn = int(rng.integers(0, 1024))
+        noise = float(rng.choice([0.0, 0.02, 0.05, 300.0], p=[0.3, 0.3, 0.3, 0.1]))
+        bits = rng.integers(0, 2, 24).astype(np.uint8)
+        L = ref_loopback(refo, 0, [], N_id_cell=cell, N_rb_dl=nrb, fs=FS[nrb], N_ant=nant, bch=dict(bits=bits, sfn=sfn), noise=noise, seed=1000 + t)
+        sf = refo.Subframe(); sf.clear()
+        L["phy"].get_dl_subframe_and_ce(L["i"], L["q"], 0, 0, cell, 4, sf)
+        err, na, ob, off = L["phy"].bch_decode(sf, cell)
+        e, a, got, o = port.bch_channel_decode(sf.rx_symb_re.copy(), sf.rx_symb_im.copy(), sf.rx_ce_re.copy(), sf.rx_ce_im.copy(), nrb, cell)
+        assert (e, a) == (err, na), (t, nrb, cell, nant, noise)
+        if err == 0:
+            assert o == off and np.array_equal(got, np.asarray(ob[:24], np.uint8)), (t, nrb, cell, nant)
+            n_mib += 1
+    assert n_mib >= 15
+    n_dci = 0
+    sys.stdout.flush()
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)     # the reference prints a line per "format 0" DCI
+    try:
+        for t in range(48):
+            nrb = bands[t % 6]; cell = int(rng.integers(0, 504)); subfr = int(rng.integers(0, 10))
+            cfi = int(rng.integers(1, 4)) if nrb > 10 else int(rng.integers(2, 4))
+            n_msg = int(rng.integers(0, 4)) if nrb >= 25 else int(rng.integers(0, 2))
+            allocs, p0 = [], 0
+            for m in range(n_msg):
+                n_prb = int(rng.integers(1, max(2, nrb // 6)))
+                allocs.append(dict(rnti=int(rng.choice([0xFFFF, 0xFFFE, int(rng.integers(1, 60))])), mcs=int(rng.integers(0, 10)), N_prb=n_prb, prb0=p0))
+                p0 += n_prb
+            noise = float(rng.choice([0.0, 0.03, 0.1, 0.6]))
+            L = ref_loopback(refo, subfr, [], N_id_cell=cell, N_rb_dl=nrb, fs=FS[nrb], N_ant=1, pdcch=dict(cfi=cfi, allocs=allocs), noise=noise, seed=2000 + t)
+            sf = refo.Subframe(); sf.clear()
+            L["phy"].get_dl_subframe_and_ce(L["i"], L["q"], 0, subfr, cell, 1, sf)
+            err, rcfi, nsym, ral = L["phy"].pdcch_decode2(sf, cell, 1)
+            r = port.pdcch_channel_decode(sf.rx_symb_re.copy(), sf.rx_symb_im.copy(), sf.rx_ce_re[0].copy(), sf.rx_ce_im[0].copy(), nrb, cell, 1, subfr)
+            tag = (t, nrb, cell, cfi, subfr, n_msg, noise)
+            assert (r["err"], r["cfi"], r["N_symbs"], len(r["allocs"])) == (err, rcfi, nsym, len(ral)), tag
+            for a, want in zip(r["allocs"], ral):
+                assert np.array_equal(alloc_row(a), alloc_row(want)), tag
+            n_dci += len(ral)
+    finally:
+        os.dup2(saved, 1); os.close(devnull); os.close(saved)
+    assert n_dci >= 24
