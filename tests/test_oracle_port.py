@@ -227,3 +227,42 @@ def test_front_end_and_pdsch_against_live_reference_random_configs(port, refo):
         else:
             seen_fail += 1
     assert seen_ok >= 15 and seen_fail >= 3, (seen_ok, seen_fail)          # the draw exercises both the decoding branch and DECODE_FAIL
+
+
+def test_cell_search_against_live_reference(port, refo):
+    """Cell search of the port against the reference itself on frames built by the reference's transmitter (CRS + PSS + SSS, random cell,
+    timing offset, carrier offset, noise): coarse timing (liblte_phy.cc:5697-5852), PSS + fine timing (:5306-5510), SSS (:5578-5686).
+    Every integer decision (peak count, symbol starts, N_id_2, PSS symbol, N_id_1, frame start) is equal; floats within 1e-4 relative
+    (the port's DFT is double precision), the coarse frequency estimate within 1 Hz."""
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    rng = np.random.default_rng(77)
+    cases = ((101, 2, 777, 30.72, 100, 4, 0.05, 0.0), (7, 1, 3000, 7.68, 25, 2, 0.05, 0.0), (55, 0, 123, 1.92, 6, 0, 0.1, 300.0), (167, 1, 2048, 15.36, 50, 3, 0.02, -900.0))
+    for (nid1, nid2, off, fs, nrb, fsi_, noise, cfo) in cases:
+        cell = 3 * nid1 + nid2
+        phy = refo.RefPhy(fs=fs, N_id_cell=cell, N_ant=1, N_rb_dl=nrb)
+        n_sf = 1920 << fsi_
+        sig_i = np.zeros(off + 21 * n_sf + 8192, np.float32); sig_q = np.zeros_like(sig_i)
+        for k in range(21):
+            sf = refo.Subframe(); sf.clear(); sf.set_num(k % 10)
+            phy.map_crs(sf, cell, 1)
+            if k % 10 in (0, 5):
+                phy.map_pss(sf, nid2, 1); phy.map_sss(sf, nid1, nid2, 1)
+            a, b = phy.create_dl_subframe(sf, 0, n_sf)
+            sig_i[off + k * n_sf: off + (k + 1) * n_sf] = a; sig_q[off + k * n_sf: off + (k + 1) * n_sf] = b
+        z = sig_i + 1j * sig_q
+        z = z * np.exp(2j * np.pi * cfo * np.arange(z.size) / (fs * 1e6))
+        z = z + noise * np.abs(z).max() * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+        i_s = np.ascontiguousarray(z.real.astype(np.float32)); q_s = np.ascontiguousarray(z.imag.astype(np.float32))
+        tag = (nid1, nid2, off, fs)
+        err, fo_r, ss_r, n_r = phy.find_coarse_timing(i_s, q_s, 20)
+        fo, ss, n = port.find_coarse_timing(i_s, q_s, fsi_, 20)
+        assert err == 0 and n == n_r and np.array_equal(ss[:n], np.asarray(ss_r)[:n]), tag
+        assert np.allclose(fo[:n], np.asarray(fo_r)[:n], atol=1.0), tag
+        err, ss2_r, nid2_r, ps_r, th_r, f_r = phy.find_pss(i_s, q_s, ss_r[0])
+        ss_p, nid2_p, ps_p, th_p, f_p = port.find_pss(i_s, q_s, fsi_, nrb, ss[0])
+        assert err == 0 and (nid2_p, ps_p, f_p) == (nid2_r, ps_r, f_r) and nid2_p == nid2 and np.array_equal(ss_p, ss2_r), tag
+        assert abs(th_p - th_r) <= 1e-4 * th_r, tag
+        err, ss3_r, nid1_r, fsi_r = phy.find_sss(i_s, q_s, nid2_r, ss2_r, th_r)
+        rc, ss_s, nid1_p, fsi_p = port.find_sss(i_s, q_s, fsi_, nrb, nid2_p, ss_p, th_p)
+        assert rc == err == 0 and nid1_p == nid1_r == nid1 and fsi_p == fsi_r and np.array_equal(ss_s, ss3_r), tag
