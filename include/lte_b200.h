@@ -79,6 +79,11 @@ int lteb200_turbo_decode(lteb200_ctx *ctx, float *d_bits, uint32_t N_d_bits, uin
 int lteb200_rate_unmatch_turbo_batch(lteb200_ctx *ctx, const float *d_e, int e_stride, int E, int K, int N_codeblocks,
                                      int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv_idx, int n_cb,
                                      float *d_out, void *stream);
+/* HOST, no device needed: the gather map the kernels above work through, as the library builds it from the reference's geometry
+ * (liblte_phy.cc:11283-11400).  first_k_out[3*i + x], 3*(K+4) entries: index of the first e-bit that lands on output d[3i+x] (-1: none
+ * within one lap of the circular buffer); every further visit comes *period e-bits later.  For inspection and CPU tests. */
+int lteb200_rate_unmatch_map(int K, int N_codeblocks, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv_idx,
+                             int32_t *first_k_out, int *period);
 /* Host twin (same argument order as the reference; dummy_bits content is ignored, only N_dummy_bits = K+4 matters). */
 int lteb200_rate_unmatch_turbo(lteb200_ctx *ctx, const float *e_bits, uint32_t N_e_bits, const uint8_t *dummy_bits,
                                uint32_t N_dummy_bits, uint32_t N_codeblocks, uint32_t tx_mode, uint32_t N_soft,
@@ -112,6 +117,12 @@ typedef struct {
     int32_t tx_mode;
     int32_t rnti;
 } lteb200_alloc;
+
+/* HOST, no device needed: the resource elements of one allocation in the order the reference visits them (RE walk of
+ * liblte_phy.cc:3745-3802 incl. the CRS, PBCH and PSS/SSS exclusions), idx_out[r] = symbol*(12*N_rb_dl) + subcarrier; *n_out = their number
+ * (LTEB200_ERR_ARGS with *n_out set if capacity is too small).  This is the index list the symbol-level kernels gather through. */
+int lteb200_pdsch_re_indices(int N_rb_dl, int N_id_cell, int N_ant, int subfr_num, int N_pdcch_symbs, const lteb200_alloc *alloc,
+                             int32_t *idx_out, int capacity, int *n_out);
 
 /* Batched liblte_phy_pdsch_channel_decode (liblte_phy.h:906-913, liblte_phy.cc:3690-3853) for N_ant == 1 and
  * single-code-block transport blocks (the envelope in which the reference itself is correct).

@@ -159,6 +159,24 @@ static void re_walk(int N_rb_dl, int N_id_cell, int N_ant, int cls, int N_pdcch_
         }
 }
 
+// HOST, no device needed: the index list the symbol-level kernels gather through, for inspection and CPU tests
+extern "C" int lteb200_pdsch_re_indices(int N_rb_dl, int N_id_cell, int N_ant, int subfr_num, int N_pdcch_symbs, const lteb200_alloc *alloc,
+                                        int32_t *idx_out, int capacity, int *n_out)
+{
+    if (!alloc || !idx_out || !n_out || N_rb_dl < 6 || N_rb_dl > 110 || N_id_cell < 0 || N_id_cell > 503 || !(N_ant == 1 || N_ant == 2 || N_ant == 4) ||
+        subfr_num < 0 || subfr_num > 9 || N_pdcch_symbs < 0 || N_pdcch_symbs > 4 || alloc->N_prb < 1 || alloc->N_prb > N_rb_dl)
+        return LTEB200_ERR_ARGS;
+    for (int s = 0; s < 2; s++)
+        for (int j = 0; j < alloc->N_prb; j++)
+            if (alloc->prb[s][j] < 0 || alloc->prb[s][j] >= N_rb_dl) return LTEB200_ERR_ARGS;
+    std::vector<int> idx;
+    re_walk(N_rb_dl, N_id_cell, N_ant, subfr_num == 0 ? 0 : (subfr_num == 5 ? 1 : 2), N_pdcch_symbs, *alloc, idx);
+    *n_out = (int)idx.size();
+    if ((int)idx.size() > capacity) return LTEB200_ERR_ARGS;
+    std::copy(idx.begin(), idx.end(), idx_out);
+    return LTEB200_OK;
+}
+
 static int seg_params(int tbs, int *K, int *F)
 {
     // liblte_phy_code_block_segmentation, single code block (liblte_phy.cc:9781-9795)

@@ -9,6 +9,7 @@
 // the reference's visiting order (liblte_phy.cc:11407-11412), unfilled positions carry the 10000 sentinel.
 // HBM-bound: reads E floats, writes 3(K+4) floats per code block.
 #include "internal.h"
+#include <algorithm>
 
 namespace {
 
@@ -71,23 +72,23 @@ int rate_unmatch_launch_var(lteb200_ctx *ctx, const float *d_e, int e_stride, co
     return LTEB200_OK;
 }
 
-// Builds (or fetches) the gather map.  Geometry exactly as the reference computes it (liblte_phy.cc:11283-11400).
-int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type,
-                         int rv, RateUnmatchMap *out)
+// Soft-buffer size N_cb of one code block (liblte_phy.cc:11283-11310); 0 or less: bad arguments
+static int soft_buffer_size(int D, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type)
 {
-    if (D < 44 || D > 6148 || E < 0 || C < 1 || rv < 0 || rv > 3 || M_dl_harq < 1) {
-        lteb200_set_error(ctx, "rate_unmatch: bad arguments");
-        return LTEB200_ERR_ARGS;
-    }
-    const int R = (D + 31) / 32, Kpi = 32 * R, ND = Kpi - D, Kw = 3 * Kpi;
+    const int R = (D + 31) / 32, Kw = 3 * 32 * R;
     const int K_mimo = (tx_mode == 3 || tx_mode == 4 || tx_mode == 8 || tx_mode == 9) ? 2 : 1;
     const int N_ir = N_soft / (K_mimo * (M_dl_harq < 8 ? M_dl_harq : 8));
     int Ncb = Kw;
     if (chan_type == 0 || chan_type == 1) Ncb = (N_ir / C < Kw) ? N_ir / C : Kw;
-    if (Ncb <= 0) { lteb200_set_error(ctx, "rate_unmatch: empty soft buffer"); return LTEB200_ERR_ARGS; }
-    std::vector<int> key = {D, Ncb, rv};
-    auto it = ctx->rum.find(key);
-    if (it != ctx->rum.end()) { *out = it->second; return LTEB200_OK; }
+    return Ncb;
+}
+
+// Host part of the gather map: first[3i+x] = rank (among the non-<NULL> circular-buffer positions, starting at k0 of redundancy version rv)
+// of the first e-bit that lands on output d[3i+x], -1 if none does within one lap.  Returns the number of ranks = the period after which
+// the circular buffer wraps onto the same outputs again.  Geometry exactly as the reference computes it (liblte_phy.cc:11283-11400).
+static int build_first_map(int D, int Ncb, int rv, std::vector<int32_t> &first)
+{
+    const int R = (D + 31) / 32, Kpi = 32 * R, ND = Kpi - D, Kw = 3 * Kpi;
     const int k0 = (int)(R * (2 * ceilf((float)Ncb / (float)(8 * R)) * rv + 2));
     // circular-buffer position -> (stream x, index t in the padded stream); t < ND are the <NULL> pads
     std::vector<int> sx(Kw), st(Kw);
@@ -99,13 +100,47 @@ int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int
         sx[Kpi + 2 * n] = 1; st[Kpi + 2 * n] = t01;
         sx[Kpi + 2 * n + 1] = 2; st[Kpi + 2 * n + 1] = t2;
     }
-    std::vector<int32_t> first(3 * D, -1);
+    first.assign(3 * (size_t)D, -1);
     int rank = 0;
     for (int j = 0; j < Ncb; j++) {
         const int pos = (k0 + j) % Ncb;
         if (st[pos] < ND) continue;
         first[3 * (st[pos] - ND) + sx[pos]] = rank++;
     }
+    return rank;
+}
+
+// HOST, no device needed: the table above for inspection and CPU tests
+extern "C" int lteb200_rate_unmatch_map(int K, int N_codeblocks, int tx_mode, int N_soft, int M_dl_harq, int chan_type, int rv_idx,
+                                        int32_t *first_k_out, int *period)
+{
+    const int D = K + 4;
+    if (!first_k_out || !period || D < 44 || D > 6148 || N_codeblocks < 1 || rv_idx < 0 || rv_idx > 3 || M_dl_harq < 1) return LTEB200_ERR_ARGS;
+    const int Ncb = soft_buffer_size(D, N_codeblocks, tx_mode, N_soft, M_dl_harq, chan_type);
+    if (Ncb <= 0) return LTEB200_ERR_ARGS;
+    std::vector<int32_t> first;
+    const int rank = build_first_map(D, Ncb, rv_idx, first);
+    if (rank == 0) return LTEB200_ERR_ARGS;
+    std::copy(first.begin(), first.end(), first_k_out);
+    *period = rank;
+    return LTEB200_OK;
+}
+
+// Builds (or fetches) the gather map on the device.
+int rate_unmatch_get_map(lteb200_ctx *ctx, int D, int E, int C, int tx_mode, int N_soft, int M_dl_harq, int chan_type,
+                         int rv, RateUnmatchMap *out)
+{
+    if (D < 44 || D > 6148 || E < 0 || C < 1 || rv < 0 || rv > 3 || M_dl_harq < 1) {
+        lteb200_set_error(ctx, "rate_unmatch: bad arguments");
+        return LTEB200_ERR_ARGS;
+    }
+    const int Ncb = soft_buffer_size(D, C, tx_mode, N_soft, M_dl_harq, chan_type);
+    if (Ncb <= 0) { lteb200_set_error(ctx, "rate_unmatch: empty soft buffer"); return LTEB200_ERR_ARGS; }
+    std::vector<int> key = {D, Ncb, rv};
+    auto it = ctx->rum.find(key);
+    if (it != ctx->rum.end()) { *out = it->second; return LTEB200_OK; }
+    std::vector<int32_t> first;
+    const int rank = build_first_map(D, Ncb, rv, first);
     if (rank == 0) { lteb200_set_error(ctx, "rate_unmatch: no transmittable position"); return LTEB200_ERR_ARGS; }
     RateUnmatchMap m;
     m.n_nonnull = rank;

@@ -1,0 +1,109 @@
+"""Host logic of the product that needs no device: the tables the symbol-level and rate-unmatching kernels work through are built on
+the host (openlte_b200/csrc/pdsch.cu: re_walk, rate_unmatch.cu: build_first_map) and exported for inspection.  Here they are compared
+with the oracle's restatement of the reference's loops (which tests/test_oracle_port.py pins to the reference itself)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+import openlte_b200
+from openlte_b200.lib import Alloc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def product_re_indices(lib, n_rb, cell, n_ant, subfr, cfi, prb0, prb1):
+    al = Alloc.make(1, prb0, 100, 1, prb_slot1=prb1)
+    out = np.zeros(14 * 12 * len(prb0), np.int32); n = C.c_int(0)
+    rc = lib.pdsch_re_indices(n_rb, cell, n_ant, subfr, cfi, C.byref(al), out.ctypes.data_as(C.c_void_p), out.size, C.byref(n))
+    assert rc == 0
+    return out[:n.value]
+
+
+def test_pdsch_re_index_lists_equal_the_oracle_walk(port):
+    """RE walk of liblte_phy.cc:3745-3802 (CRS of 1 / 2 / 4 ports, PBCH in subframe 0, PSS/SSS in subframes 0 and 5, control symbols):
+    every bandwidth, random PRB sets that differ between the slots, random cells, all subframe numbers."""
+    lib = openlte_b200.load()
+    rng = np.random.default_rng(31)
+    n_checked = 0
+    for n_rb in (6, 15, 25, 50, 75, 100):
+        nsc = 12 * n_rb
+        for trial in range(40):
+            cell = int(rng.integers(0, 504)); n_ant = int(rng.choice([1, 2, 4])); subfr = int(rng.integers(0, 10)); cfi = int(rng.integers(1, 5))
+            n_prb = int(rng.integers(1, n_rb + 1))
+            prb0 = np.sort(rng.choice(n_rb, n_prb, replace=False)).astype(np.int32)
+            prb1 = prb0 if trial % 3 else rng.permutation(prb0).astype(np.int32)          # distributed-style: other PRBs in slot 1
+            if trial % 5 == 0:   # make sure the centre band (PBCH / PSS / SSS exclusions) is hit
+                prb0 = np.arange(n_rb, dtype=np.int32); prb1 = prb0
+            want = port.pdsch_re_indices(n_rb, cell, n_ant, subfr, cfi, prb0, prb1)
+            got = product_re_indices(lib, n_rb, cell, n_ant, subfr, cfi, prb0, prb1)
+            want = (want // 1200) * nsc + want % 1200                                   # the oracle addresses rows of 1200 subcarriers
+            assert np.array_equal(got, want), (n_rb, cell, n_ant, subfr, cfi, len(prb0))
+            assert got.size == np.unique(got).size and (got // nsc >= cfi).all()
+            n_checked += 1
+    assert n_checked == 240
+    # argument checks
+    al = Alloc.make(1, [0, 200], 100, 1); out = np.zeros(4000, np.int32); n = C.c_int(0)
+    assert lib.pdsch_re_indices(100, 0, 1, 1, 2, C.byref(al), out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)) == -1       # PRB out of range
+    al = Alloc.make(1, [0, 1], 100, 1)
+    assert lib.pdsch_re_indices(100, 0, 3, 1, 2, C.byref(al), out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)) == -1       # 3 ports
+    assert lib.pdsch_re_indices(100, 0, 1, 1, 2, C.byref(al), out.ctypes.data_as(C.c_void_p), 10, C.byref(n)) == -1 and n.value > 10   # capacity
+
+
+def unmatch_through_map(first, period, e, D):
+    """What rate_unmatch_kernel does with the map (one output per thread: first visit, then one every `period` e-bits, soft combining with
+    the reference's sentinel rules, liblte_phy.cc:11407-11412), in numpy float32."""
+    E = e.size
+    out = np.full(3 * D, 10000.0, np.float32)
+    k = first.astype(np.int64).copy()
+    live = (k >= 0) & (k < E)
+    first_visit = True
+    while live.any():
+        v = e[k[live]]
+        w = out[live]
+        if first_visit:
+            w = v.copy()
+        else:
+            at_null = w == np.float32(10000.0)
+            add = (~at_null) & (v != np.float32(10000.0))
+            w = np.where(at_null, v, np.where(add, (w + v).astype(np.float32), w)).astype(np.float32)
+        out[live] = w
+        first_visit = False
+        k = k + period
+        live = live & (k < E)
+    return out
+
+
+def test_rate_unmatch_map_equals_the_oracle_for_every_block_size(port):
+    """Gather map of every legal block size and redundancy version (sub-block interleaver, <NULL> pads, k0, circular-buffer wrap,
+    liblte_phy.cc:11283-11400): applying it to punctured, exact and repeated e-sequences (with sentinel entries among them) gives exactly
+    what the oracle's restatement of liblte_phy_rate_unmatch_turbo gives."""
+    lib = openlte_b200.load()
+    rows = re.findall(r"\{\s*(\d+),\s*(\d+),\s*(\d+)\}", open(os.path.join(HERE, "..", "openlte_b200", "csrc", "qpp_table.h")).read())
+    Ks = [int(a) for a, _, _ in rows]
+    assert len(Ks) == 188
+    rng = np.random.default_rng(9)
+    for n, K in enumerate(Ks):
+        D = K + 4
+        for rv in range(4):
+            first = np.zeros(3 * D, np.int32); period = C.c_int(0)
+            assert lib.rate_unmatch_map(K, 1, 1, 250368, 8, 0, rv, first.ctypes.data_as(C.c_void_p), C.byref(period)) == 0
+            assert period.value == 3 * D                                   # one lap visits every non-<NULL> position once (N_cb = K_w here)
+            assert np.array_equal(np.sort(first), np.arange(3 * D))       # ... so the map is a permutation
+            if (n + rv) % 4:
+                continue                                                  # the numeric comparison on every fourth (size, rv) pair
+            for E in (2 * D + 7, 3 * D, 7 * D + 11):
+                e = np.round(rng.standard_normal(E) * 20).astype(np.float32)
+                e[rng.integers(0, E, E // 17)] = 10000.0
+                want = port.rate_unmatch_turbo(e, D, rv=rv)
+                assert np.array_equal(unmatch_through_map(first, period.value, e, D), want), (K, rv, E)
+    # limited soft buffer (N_cb < K_w: category-1 UE with several code blocks): positions beyond N_cb are never sent
+    K = 6144; D = K + 4
+    first = np.zeros(3 * D, np.int32); period = C.c_int(0)
+    assert lib.rate_unmatch_map(K, 3, 1, 250368, 8, 0, 0, first.ctypes.data_as(C.c_void_p), C.byref(period)) == 0
+    assert period.value < 3 * D and (first == -1).sum() == 3 * D - period.value
+    e = np.round(rng.standard_normal(2 * D) * 20).astype(np.float32)
+    assert np.array_equal(unmatch_through_map(first, period.value, e, D), port.rate_unmatch_turbo(e, D, rv=0, C=3))
+    assert lib.rate_unmatch_map(30, 1, 1, 250368, 8, 0, 0, first.ctypes.data_as(C.c_void_p), C.byref(period)) == -1
+    assert lib.rate_unmatch_map(K, 1, 1, 250368, 8, 0, 4, first.ctypes.data_as(C.c_void_p), C.byref(period)) == -1
