@@ -180,6 +180,14 @@ int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long
                             int N_id_cell, int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf,
                             int N_pdcch_symbs, const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter,
                             uint8_t *h_tb_bits, int tb_stride, int32_t *h_crc_ok);
+/* HOST, no device needed: the plan lteb200_dl_receive_host follows for a batch.  Chunk c = subframes [bounds_out[c], bounds_out[c+1]);
+ * copy_end_out[c] = how many samples of the stream (cumulative, from sample 0) must have reached the device before chunk c's kernels
+ * start: everything its last subframe reads, i.e. start + subframe + the two look-ahead symbols of the channel estimator -- with
+ * gapped, duplicate or overlapping (non-decreasing) start indices as well.  K_first: code block size of the first allocation,
+ * n_sm: multiprocessors of the device (148 on B200), capacity: entries available in bounds_out (n_chunks + 1 needed; *n_chunks_out is
+ * set even when it does not fit).  For inspection and CPU tests. */
+int lteb200_e2e_plan(int n_sf, int n_alloc, int K_first, int turbo_mode, int n_sm, int fs_idx, long long n_samps, const long long *h_start_idx,
+                     int *bounds_out, long long *copy_end_out, int capacity, int *n_chunks_out);
 
 /* ------------------------------------------------------------------------------------------------- sync */
 /* Host twins of liblte_phy_dl_find_coarse_timing_and_freq_offset (liblte_phy.h:1134-1138, .cc:5697-5852),

@@ -199,34 +199,13 @@ extern "C" int lteb200_dl_receive_batch(lteb200_ctx *ctx, const void *d_iq, int 
     return rc;
 }
 
-// Host-pointer entry point.  The batch is cut into chunks of subframes that flow through a three-stage pipeline on
-// three streams -- H2D copy of a chunk's samples, the receive kernels, D2H copy of its transport blocks -- so that PCIe
-// traffic in both directions overlaps the kernels (pinned host buffers make the copies truly asynchronous; pageable
-// ones still work, staged by the driver).  start_idx must be non-decreasing.
-extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl, int N_id_cell,
-                                       int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf, int N_pdcch_symbs,
-                                       const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter, uint8_t *h_tb_bits, int tb_stride,
-                                       int32_t *h_crc_ok)
+// ---- host pipeline plan (pure host logic, also exported for CPU tests as lteb200_e2e_plan) -------------------------------------------
+// Chunk schedule.  Small chunks cost efficiency (partial waves, launch gaps), large ones expose the first copy in and the last
+// copy out.  LTEB200_E2E_SCHEDULE="a,b,c" forces explicit sizes, LTEB200_E2E_CHUNK=n equal chunks of n subframes (development aids).
+// Returns bounds: chunk c = subframes [bounds[c], bounds[c+1]).
+static std::vector<int> plan_chunks(int n_sf, int n_alloc, int K_first, int turbo_mode, int n_sm)
 {
-    if (!ctx || !h_iq || !h_start_idx || !h_subfr_num || !h_tb_bits || !h_crc_ok || n_sf < 1 || n_alloc < 1 || n_samps < 1 || fs_idx < 0 || fs_idx > 4)
-        return LTEB200_ERR_ARGS;
-    for (int i = 1; i < n_sf; i++)
-        if (h_start_idx[i] < h_start_idx[i - 1]) { lteb200_set_error(ctx, "dl_receive_host: start_idx must be non-decreasing"); return LTEB200_ERR_ARGS; }
-    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    const size_t samp_bytes = iq_fmt == LTEB200_IQ_I8 ? 2 : 8;
-    if (!ctx->s_h2d) {
-        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        // the decode kernels (critical path) outrank the front-end kernels of the NEXT chunk, which only fill the gaps they leave
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_comp, cudaStreamNonBlocking, prio_hi));
-        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo));
-        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    }
-    // Chunk schedule.  Small chunks cost efficiency (partial waves, launch gaps), large ones expose the first copy in and the last
-    // copy out: so the sizes ramp up 128, 256, 512, ... to a plateau and ramp down again at the end.  LTEB200_E2E_CHUNK=n forces
-    // equal chunks of n subframes (development aid).
-    std::vector<int> bounds;                     // chunk c = subframes [bounds[c], bounds[c+1])
+    std::vector<int> bounds;
     bounds.push_back(0);
     if (const char *sched = getenv("LTEB200_E2E_SCHEDULE")) {         // explicit chunk sizes "a,b,c,..." (development aid); the rest goes into a last chunk
         int pos = 0;
@@ -250,12 +229,8 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
         // whole number of decoder waves (148 SMs x resident blocks / transport blocks per subframe) so that no chunk ends in a
         // partial wave.  Measured on 4000 subframes (profiles/r2_e2e_schedule.txt): 10.8 ms in one chunk, 5.9-6.2 ms with equal or doubling chunks,
         // 5.7 ms with this schedule.
-        int K_first = 6144;
-        { AllocTables t0; if (get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[0], &t0) == LTEB200_OK) K_first = t0.K; }
         const int nt_class = mlm_size_class(K_first);
         const int blocks_per_sm = nt_class == 384 ? 2 : (nt_class == 192 ? 4 : (nt_class == 128 ? 6 : 12));
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
         int wave = (n_sm * blocks_per_sm) / n_alloc;
         if (wave < 16) wave = 16;
         // a chunk costs about 1.28 us per subframe + 0.1 ms (kernel tails, launch gaps), the copy of the next one 1.2 us per subframe: the decode
@@ -271,23 +246,98 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
                 sz = std::min(20 * wave, (int)(2.34 * sz) / wave * wave);
             }
         } else {
-        const int first = 2 * wave, cap = 12 * wave;
-        int pos = 0, sz = first;
-        while (n_sf - pos > sz + 3 * wave) {
-            pos += sz;
-            bounds.push_back(pos);
-            int nxt = (int)(1.07 * sz) + 83;
-            nxt = (nxt / wave) * wave;
-            if (nxt > cap) nxt = cap;
-            sz = nxt;
-        }
-        if (n_sf - pos > 6 * wave) { pos = n_sf - 3 * wave; bounds.push_back(pos); }
+            const int first = 2 * wave, cap = 12 * wave;
+            int pos = 0, sz = first;
+            while (n_sf - pos > sz + 3 * wave) {
+                pos += sz;
+                bounds.push_back(pos);
+                int nxt = (int)(1.07 * sz) + 83;
+                nxt = (nxt / wave) * wave;
+                if (nxt > cap) nxt = cap;
+                sz = nxt;
+            }
+            if (n_sf - pos > 6 * wave) { pos = n_sf - 3 * wave; bounds.push_back(pos); }
         }
     }
     if (bounds.back() != n_sf) bounds.push_back(n_sf);
+    return bounds;
+}
+
+// a subframe's 16 symbols end two symbols into the next subframe (the estimator's look-ahead): that halo travels with the chunk
+static inline long long e2e_halo(int fs_idx) { return 2LL * ((128LL << fs_idx) + (10LL << fs_idx)) + 16; }
+
+// One sample past the last sample chunk c's kernels may read = where the cumulative H2D copy must have got to before they start:
+// everything the chunk's LAST subframe reads (its 14 symbols + the two look-ahead symbols), and at least up to the halo of the next chunk's
+// first subframe; with gapped, duplicate or overlapping (non-decreasing) start indices the former is the larger one.  The last chunk takes
+// the rest of the stream.
+static long long chunk_copy_end(int c, const std::vector<int> &bounds, const long long *h_start_idx, int fs_idx, long long n_samps)
+{
     const int n_chunks = (int)bounds.size() - 1;
-    // a subframe's 16 symbols end two symbols into the next subframe (the estimator's look-ahead): that halo travels with the chunk
-    const long long halo = 2LL * ((128LL << fs_idx) + (10LL << fs_idx)) + 16;
+    const long long halo = e2e_halo(fs_idx);
+    long long hi = n_samps;
+    if (c + 1 < n_chunks) {
+        hi = h_start_idx[bounds[c + 1]] + halo;
+        const long long last_end = h_start_idx[bounds[c + 1] - 1] + (1920LL << fs_idx) + halo;
+        if (last_end > hi) hi = last_end;
+    }
+    if (hi > n_samps) hi = n_samps;
+    return hi;
+}
+
+// HOST, no device needed: the plan lteb200_dl_receive_host follows for a batch -- chunk boundaries and, per chunk, how far the H2D copy has to
+// have got before the chunk's kernels may start (copy_end[c], cumulative, in samples).  n_sm: multiprocessors of the device (148 on B200).
+extern "C" int lteb200_e2e_plan(int n_sf, int n_alloc, int K_first, int turbo_mode, int n_sm, int fs_idx, long long n_samps, const long long *h_start_idx,
+                                int *bounds_out, long long *copy_end_out, int capacity, int *n_chunks_out)
+{
+    if (n_sf < 1 || n_alloc < 1 || K_first < 40 || K_first > 6144 || n_sm < 1 || fs_idx < 0 || fs_idx > 4 || n_samps < 1 || !h_start_idx || !bounds_out ||
+        !copy_end_out || !n_chunks_out)
+        return LTEB200_ERR_ARGS;
+    for (int i = 1; i < n_sf; i++) if (h_start_idx[i] < h_start_idx[i - 1]) return LTEB200_ERR_ARGS;
+    const std::vector<int> bounds = plan_chunks(n_sf, n_alloc, K_first, turbo_mode, n_sm);
+    const int n_chunks = (int)bounds.size() - 1;
+    *n_chunks_out = n_chunks;
+    if (n_chunks + 1 > capacity) return LTEB200_ERR_ARGS;
+    long long copied = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        bounds_out[c] = bounds[c];
+        const long long hi = chunk_copy_end(c, bounds, h_start_idx, fs_idx, n_samps);
+        if (hi > copied) copied = hi;
+        copy_end_out[c] = copied;
+    }
+    bounds_out[n_chunks] = bounds[n_chunks];
+    return LTEB200_OK;
+}
+
+// Host-pointer entry point.  The batch is cut into chunks of subframes that flow through a three-stage pipeline on
+// three streams -- H2D copy of a chunk's samples, the receive kernels, D2H copy of its transport blocks -- so that PCIe
+// traffic in both directions overlaps the kernels (pinned host buffers make the copies truly asynchronous; pageable
+// ones still work, staged by the driver).  start_idx must be non-decreasing.
+extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int iq_fmt, long long n_samps, int fs_idx, int N_rb_dl, int N_id_cell,
+                                       int N_ant, const long long *h_start_idx, const int *h_subfr_num, int n_sf, int N_pdcch_symbs,
+                                       const lteb200_alloc *allocs, int n_alloc, int turbo_mode, int n_iter, uint8_t *h_tb_bits, int tb_stride,
+                                       int32_t *h_crc_ok)
+{
+    if (!ctx || !h_iq || !h_start_idx || !h_subfr_num || !allocs || !h_tb_bits || !h_crc_ok || n_sf < 1 || n_alloc < 1 || n_samps < 1 || fs_idx < 0 || fs_idx > 4)
+        return LTEB200_ERR_ARGS;
+    for (int i = 1; i < n_sf; i++)
+        if (h_start_idx[i] < h_start_idx[i - 1]) { lteb200_set_error(ctx, "dl_receive_host: start_idx must be non-decreasing"); return LTEB200_ERR_ARGS; }
+    LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t samp_bytes = iq_fmt == LTEB200_IQ_I8 ? 2 : 8;
+    if (!ctx->s_h2d) {
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        // the decode kernels (critical path) outrank the front-end kernels of the NEXT chunk, which only fill the gaps they leave
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_comp, cudaStreamNonBlocking, prio_hi));
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo));
+        LTE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    int K_first = 6144;
+    { AllocTables t0; if (get_alloc_tables(ctx, N_rb_dl, N_id_cell, N_ant, N_pdcch_symbs, allocs[0], &t0) == LTEB200_OK) K_first = t0.K; }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const std::vector<int> bounds = plan_chunks(n_sf, n_alloc, K_first, turbo_mode, n_sm);      // chunk c = subframes [bounds[c], bounds[c+1])
+    const int n_chunks = (int)bounds.size() - 1;
     StreamScope scope;                 // every event and stream-ordered allocation below is released on every exit path
     std::vector<cudaEvent_t> ev_h(n_chunks), ev_c(n_chunks), ev_f(n_chunks);
     for (int c = 0; c < n_chunks; c++) {
@@ -316,15 +366,7 @@ extern "C" int lteb200_dl_receive_host(lteb200_ctx *ctx, const void *h_iq, int i
     // stage 1: sample slices, back to back.  Chunk c's copy ends `halo` samples into chunk c+1; the next copy continues from there.
     long long copied = 0;
     for (int c = 0; c < n_chunks; c++) {
-        // everything the chunk's LAST subframe reads (its 14 symbols + the two look-ahead symbols), and at least up to the halo of the
-        // next chunk's first subframe: with gapped, duplicate or overlapping start indices the former is the larger one
-        long long hi = n_samps;
-        if (c + 1 < n_chunks) {
-            hi = h_start_idx[bounds[c + 1]] + halo;
-            const long long last_end = h_start_idx[bounds[c + 1] - 1] + (1920LL << fs_idx) + halo;
-            if (last_end > hi) hi = last_end;
-        }
-        if (hi > n_samps) hi = n_samps;
+        const long long hi = chunk_copy_end(c, bounds, h_start_idx, fs_idx, n_samps);
         if (hi > copied) {
             LTE_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_iq + samp_bytes * copied, (const char *)h_iq + samp_bytes * copied, samp_bytes * (size_t)(hi - copied),
                                             cudaMemcpyHostToDevice, ctx->s_h2d));

@@ -90,6 +90,7 @@ SYMBOLS = {
     "lteb200_pdcch_cce_map": (_i, [_i, _i, _i, _i, _f, _vp]),
     "lteb200_pdsch_re_indices": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "lteb200_rate_unmatch_map": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lteb200_e2e_plan": (_i, [_i, _i, _i, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp]),
     "lteb200_pdcch_unpack": (_i, [_vp, _i, _i, _vp, _vp]),
     "lteb200_pdcch_channel_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u32, _u32, C.c_uint8, _f, _i, _vp, _vp, _vp, _vp]),
     "lteb200_dl_scan_batch": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp]),

@@ -107,3 +107,75 @@ def test_rate_unmatch_map_equals_the_oracle_for_every_block_size(port):
     assert np.array_equal(unmatch_through_map(first, period.value, e, D), port.rate_unmatch_turbo(e, D, rv=0, C=3))
     assert lib.rate_unmatch_map(30, 1, 1, 250368, 8, 0, 0, first.ctypes.data_as(C.c_void_p), C.byref(period)) == -1
     assert lib.rate_unmatch_map(K, 1, 1, 250368, 8, 0, 4, first.ctypes.data_as(C.c_void_p), C.byref(period)) == -1
+
+
+def e2e_plan(lib, n_sf, n_alloc, K, mode, starts, fs_idx=4, n_samps=None, n_sm=148):
+    starts = np.ascontiguousarray(starts, np.int64)
+    if n_samps is None:
+        n_samps = int(starts[-1]) + (1920 << fs_idx) + 8192
+    bounds = np.zeros(n_sf + 2, np.int32); ends = np.zeros(n_sf + 2, np.int64); n = C.c_int(0)
+    rc = lib.e2e_plan(n_sf, n_alloc, K, mode, n_sm, fs_idx, n_samps, starts.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p),
+                      ends.ctypes.data_as(C.c_void_p), bounds.size, C.byref(n))
+    assert rc == 0
+    return bounds[:n.value + 1].copy(), ends[:n.value].copy(), n_samps
+
+
+def test_host_pipeline_plan():
+    """Chunk schedule and copy bounds of lteb200_dl_receive_host (capi_chain.cu: plan_chunks, chunk_copy_end) without a device: the shipped
+    schedule for the bench workload is the one measured in profiles/r2_e2e_schedule.txt; chunks tile the batch; and before a chunk's kernels
+    start, the cumulative copy covers everything each of its subframes reads -- with contiguous, gapped, duplicate and overlapping start
+    indices (the round-1 advisor's race)."""
+    lib = openlte_b200.load()
+    for v in ("LTEB200_E2E_SCHEDULE", "LTEB200_E2E_CHUNK"):
+        os.environ.pop(v, None)
+    n_sf_samps = 30720
+    starts = np.arange(4000, dtype=np.int64) * n_sf_samps
+    # the bench workload: 4000 subframes x 4 transport blocks of K = 6144 -> wave = 148 SMs x 2 blocks / 4 = 74 subframes
+    b, ends, n_samps = e2e_plan(lib, 4000, 4, 6144, 1, starts)
+    assert len(b) - 1 == 10 and b[1] == 148                                    # "10 chunks, first 148 subframes" in the measured trace
+    sizes = np.diff(b)
+    assert (sizes[:-2] % 74 == 0).all() and sizes.max() <= 12 * 74 and sizes[-1] == 3 * 74 and (np.diff(sizes[:-2]) >= 0).all()
+    # the reference-exact decoder gets few large chunks: 6, 14, 20 waves (profiles/r2_bench_mode_a.json)
+    b0, _, _ = e2e_plan(lib, 4000, 4, 6144, 0, starts)
+    assert np.diff(b0)[:3].tolist() == [444, 1036, 1480] and len(b0) - 1 <= 5
+    # small batches: one chunk
+    b1, e1, ns1 = e2e_plan(lib, 100, 4, 6144, 1, starts[:100])
+    assert b1.tolist() == [0, 100] and e1.tolist() == [ns1]
+    rng = np.random.default_rng(12)
+    look = {4: 2048 + 160 + 2048 + 144}                                       # two look-ahead symbols at 30.72 Msps (liblte_phy.cc:5946-5957)
+    for trial in range(60):
+        n_sf = int(rng.integers(1, 9000)); n_alloc = int(rng.integers(1, 9)); K = int(rng.choice([40, 1024, 2048, 3072, 6144])); mode = int(rng.integers(0, 2))
+        kind = trial % 4
+        if kind == 0:
+            st = np.arange(n_sf, dtype=np.int64) * n_sf_samps + int(rng.integers(0, 5000))
+        elif kind == 1:      # gaps
+            st = np.cumsum(n_sf_samps + rng.integers(0, 3 * n_sf_samps, n_sf)).astype(np.int64)
+        elif kind == 2:      # duplicates and overlaps
+            st = np.cumsum(rng.choice([0, 17, 1000, n_sf_samps], n_sf)).astype(np.int64)
+        else:                # long runs of one index, then a jump
+            st = np.repeat(np.arange((n_sf + 99) // 100, dtype=np.int64) * 5 * n_sf_samps, 100)[:n_sf]
+        n_samps = int(st[-1]) + n_sf_samps + int(rng.choice([0, 100, 4400, 9000]))      # streams that end inside the last look-ahead too
+        b, ends, _ = e2e_plan(lib, n_sf, n_alloc, K, mode, st, n_samps=n_samps)
+        assert b[0] == 0 and b[-1] == n_sf and (np.diff(b) > 0).all(), (trial, b)
+        assert (np.diff(ends) >= 0).all() and ends[-1] == n_samps
+        for c in range(len(b) - 1):
+            need = min(n_samps, int(st[b[c]:b[c + 1]].max()) + n_sf_samps + look[4])
+            assert ends[c] >= need, (trial, kind, c, ends[c], need)
+    # development overrides
+    os.environ["LTEB200_E2E_CHUNK"] = "64"
+    try:
+        b, _, _ = e2e_plan(lib, 1000, 4, 6144, 1, starts[:1000])
+        assert np.diff(b).tolist() == [64] * 15 + [40]
+    finally:
+        os.environ.pop("LTEB200_E2E_CHUNK", None)
+    os.environ["LTEB200_E2E_SCHEDULE"] = "592,1480,1480"
+    try:
+        b, _, _ = e2e_plan(lib, 4000, 4, 6144, 0, starts)
+        assert np.diff(b).tolist() == [592, 1480, 1480, 448]
+    finally:
+        os.environ.pop("LTEB200_E2E_SCHEDULE", None)
+    # refusals: decreasing start indices, no room for the result
+    bad = starts[:10].copy(); bad[5] = 0
+    bounds = np.zeros(12, np.int32); ends = np.zeros(12, np.int64); n = C.c_int(0)
+    assert lib.e2e_plan(10, 4, 6144, 1, 148, 4, 10 ** 7, bad.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), ends.ctypes.data_as(C.c_void_p), 12, C.byref(n)) == -1
+    assert lib.e2e_plan(4000, 4, 6144, 1, 148, 4, 4000 * 30720 + 8192, starts.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), ends.ctypes.data_as(C.c_void_p), 5, C.byref(n)) == -1 and n.value == 10
