@@ -179,3 +179,11 @@ def test_host_pipeline_plan():
     bounds = np.zeros(12, np.int32); ends = np.zeros(12, np.int64); n = C.c_int(0)
     assert lib.e2e_plan(10, 4, 6144, 1, 148, 4, 10 ** 7, bad.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), ends.ctypes.data_as(C.c_void_p), 12, C.byref(n)) == -1
     assert lib.e2e_plan(4000, 4, 6144, 1, 148, 4, 4000 * 30720 + 8192, starts.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), ends.ctypes.data_as(C.c_void_p), 5, C.byref(n)) == -1 and n.value == 10
+
+
+def test_dci_1a_transport_block_sizes(port):
+    """lteb200_dci_1a_tbs (what the device transmitter announces in a DCI 1A) against the oracle's copy of the reference's table
+    (36.213 table 7.1.7.2.1-1 column 3 as liblte_phy.cc:13273-13380 indexes it), which tests/test_control_oracle.py pins to the reference."""
+    lib = openlte_b200.load()
+    assert [lib.dci_1a_tbs(m) for m in range(27)] == [port.tbs_1a(m, 3) for m in range(27)]
+    assert lib.dci_1a_tbs(27) == -1 and lib.dci_1a_tbs(-1) == -1
