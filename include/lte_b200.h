@@ -18,6 +18,13 @@
  *
  * All functions return LTEB200_OK (0) or a negative LTEB200_ERR_*; lteb200_last_error() gives the text.
  * There is NO CPU fallback: without a CUDA device every compute entry point fails with LTEB200_ERR_CUDA.
+ * Functions marked HOST below are table builders that need neither a device nor a context.
+ *
+ * Threads and streams.  A context is used by ONE thread at a time, like a LIBLTE_PHY_STRUCT (its table caches, scratch arena and
+ * last-error text are not locked); different contexts may be used from different threads concurrently (the one process-wide cache,
+ * the per-allocation index tables, is locked).  *_batch calls enqueue their kernels on the caller's stream and return without
+ * waiting for them; the first call with a new block size, cell or allocation also builds that table (a synchronous upload).  The
+ * host-pointer twins and lteb200_dl_receive_host return when their results are in the caller's buffers.
  */
 #ifndef LTE_B200_H
 #define LTE_B200_H
