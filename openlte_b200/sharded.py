@@ -27,30 +27,43 @@ def receive_sharded(iq, params, decode_fn, out_shape, device, distribute="broadc
     dist.broadcast(hdr, 0, group=group)
     n_samps, n_sf, first_subfr, fs_idx = (int(x) for x in hdr.tolist())
     lo, hi = shard.shard_range(n_sf, rank, world)
-    s_lo, s_hi, starts = shard.shard_samples(n_sf, rank, world, fs_idx)
-    s_hi = min(s_hi, n_samps)
+
+    def span(r):
+        """sample range of rank r, clipped to the stream; (0, 0) for a rank without subframes (more ranks than subframes)"""
+        l, h = shard.shard_range(n_sf, r, world)
+        if h == l:
+            return 0, 0
+        a, b, _ = shard.shard_samples(n_sf, r, world, fs_idx)
+        return min(a, n_samps), min(b, n_samps)
+
+    s_lo, s_hi = span(rank)
+    starts = shard.shard_samples(n_sf, rank, world, fs_idx)[2]
     if distribute == "broadcast":
         buf = iq if rank == 0 else torch.empty((n_samps, 2), dtype=torch.int8, device=device)
         dist.broadcast(buf, 0, group=group)
         mine = buf[s_lo:s_hi]
     else:
-        spans = [shard.shard_samples(n_sf, r, world, fs_idx)[:2] for r in range(world)]
-        width = max(min(b, n_samps) - a for a, b in spans)
+        spans = [span(r) for r in range(world)]
+        width = max(1, max(b - a for a, b in spans))
         mine_pad = torch.zeros((width, 2), dtype=torch.int8, device=device)
         if rank == 0:
             parts = []
             for a, b in spans:
                 p = torch.zeros((width, 2), dtype=torch.int8, device=device)
-                p[: min(b, n_samps) - a] = iq[a:min(b, n_samps)]
+                p[: b - a] = iq[a:b]
                 parts.append(p)
             dist.scatter(mine_pad, parts, src=0, group=group)
         else:
             dist.scatter(mine_pad, None, src=0, group=group)
         mine = mine_pad[: s_hi - s_lo]
-    tb, ok = decode_fn(mine, starts, shard.subframe_numbers(first_subfr, lo, hi))
+    if hi > lo:
+        tb, ok = decode_fn(mine, starts, shard.subframe_numbers(first_subfr, lo, hi))
+    else:       # nothing to do on this rank; it still takes part in the gather
+        tb = torch.zeros((0,) + tuple(out_shape), dtype=torch.uint8, device=device)
+        ok = torch.zeros((0, out_shape[0]), dtype=torch.int32, device=device)
     # gather in stream order (shards differ by at most one subframe: pad to the largest)
     sizes = [shard.shard_range(n_sf, r, world) for r in range(world)]
-    pad = max(h - l for l, h in sizes)
+    pad = max(1, max(h - l for l, h in sizes))
     tb_pad = torch.zeros((pad,) + tuple(out_shape), dtype=torch.uint8, device=device)
     ok_pad = torch.zeros((pad, out_shape[0]), dtype=torch.int32, device=device)
     tb_pad[: hi - lo] = tb

@@ -93,6 +93,15 @@ WORKER2 = textwrap.dedent("""
         if rank == 0:
             want_tb, want_ok = decode(stream, [i * 1920 for i in range(n_sf)], shard.subframe_numbers(first, 0, n_sf))
             assert torch.equal(tb, want_tb) and torch.equal(ok, want_ok), mode
+    # more ranks than subframes (rank 1 holds nothing, still joins the collectives), and a stream that ends inside the last halo
+    short = stream[: 1920 + 100] if rank == 0 else None
+    for mode in ("broadcast", "scatter"):
+        tb, ok = sharded.receive_sharded(short, dict(n_sf=1, first_subfr=3, fs_idx=fs_idx) if rank == 0 else None, decode, (2, 4), "cpu", distribute=mode)
+        if rank == 0:
+            want_tb, want_ok = decode(short, [0], [3])
+            assert tuple(tb.shape) == (1, 2, 4) and torch.equal(tb, want_tb) and torch.equal(ok, want_ok), mode
+        else:
+            assert tb is None and ok is None
     if rank == 0:
         print("SHARDED_OK")
     dist.destroy_process_group()
