@@ -331,7 +331,8 @@ enum { LTEB200_DEMAP_REFERENCE = 0, LTEB200_DEMAP_MAXLOG = 1 };
  * bit per byte like the reference's out_bits (liblte_phy.h:906-913).  PACKED: eight bits per byte, first bit in the MSB -- an eighth of the
  * device-to-host traffic; tb_stride is then in bytes of packed data (>= tbs / 8).  PACKED needs transport blocks without filler bits (tbs + 24 a
  * turbo block size), with the max-log-MAP decoder also a block size that is a multiple of 32, and an allocation the symbol-level kernel takes
- * whole (no ragged multi-port tail, soft bits within its shared-memory staging); it is refused otherwise. */
+ * whole (no ragged multi-port tail, soft bits within its shared-memory staging); it is refused otherwise.  lteb200_dl_scan_batch and the
+ * host twin lteb200_pdsch_channel_decode always return one bit per byte (their outputs are defined that way), whatever is set here. */
 enum { LTEB200_TB_BYTES = 0, LTEB200_TB_PACKED = 1 };
 int lteb200_set_tb_format(lteb200_ctx *ctx, int format);
 int lteb200_set_demapper(lteb200_ctx *ctx, int demap);

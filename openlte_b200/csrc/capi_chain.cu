@@ -140,6 +140,7 @@ extern "C" int lteb200_pdsch_channel_decode(lteb200_ctx *ctx, const float *rx_sy
 {
     // entry default of the reference: INVALID_INPUTS (liblte_phy.cc:3699-3705)
     if (!ctx || !rx_symb_re || !rx_symb_im || !rx_ce_re || !rx_ce_im || !alloc || !out_bits || !N_out_bits || N_id_cell > 503) return LTEB200_ERR_ARGS;
+    TbBytesScope bytes_out(ctx);     // out_bits is one bit per byte like the reference's, whatever the context's transport-block format
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     const int nsc = 12 * N_rb_dl;
     float *d_in = nullptr, *d_grid = nullptr, *d_ce = nullptr;

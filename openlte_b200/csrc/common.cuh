@@ -64,6 +64,15 @@ struct lteb200_ctx {
     unsigned long long launches;
 };
 
+// Entry points whose results are DEFINED as one bit per byte (the scan's tb_bits, the host twins' out_bits -- liblte_phy.h:906-913) run
+// with the byte format whatever lteb200_set_tb_format says; the caller's choice is restored on every exit path.
+struct TbBytesScope {
+    lteb200_ctx *c;
+    int saved;
+    explicit TbBytesScope(lteb200_ctx *ctx) : c(ctx), saved(ctx->tb_packed) { c->tb_packed = 0; }
+    ~TbBytesScope() { c->tb_packed = saved; }
+};
+
 // Returns a device pointer to `bytes` of scratch; grows (synchronously) when needed.
 int lteb200_arena(lteb200_ctx *ctx, size_t bytes, void **ptr);
 

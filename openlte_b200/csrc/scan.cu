@@ -32,6 +32,7 @@ extern "C" int lteb200_dl_scan_batch(lteb200_ctx *ctx, const void *d_iq, int iq_
     if (n_sf > 65535) { lteb200_set_error(ctx, "at most 65535 subframes per call (split the batch)"); return LTEB200_ERR_ARGS; }
     cudaStream_t stream = (cudaStream_t)stream_;
     StreamScope scope;               // stream-ordered temporaries are released on every exit path
+    TbBytesScope bytes_out(ctx);     // tb_bits is one bit per byte, whatever the context's transport-block format
     LTE_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     *tb_used = 0;
     const int nsc = 12 * N_rb_dl;
