@@ -381,7 +381,7 @@ int ref_chain_pool(int n_threads, int fs_enum, int N_rb_dl, int N_id_cell, int c
     std::atomic<bool> go(false);
     auto body = [&](int t) {
         Worker &me = w[t];
-        {
+        if (n_sf > 0) {
             /* untimed warm-up on this thread: one subframe through both stages, so that the first-touch page faults of the 44 MB scratch
              * struct (zero pages until written) and the cold instruction/data caches are not charged to the reference */
             const int sn = subfr_num[0];
