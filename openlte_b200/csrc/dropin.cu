@@ -204,8 +204,10 @@ static uint32 k_below(uint32 kp)
 static uint32 crc24b(const uint8 *bits, uint32 n)
 {
     uint32 rem = 0;
-    for (uint32 i = 0; i < n + 24; i++) { rem = (rem << 1) | (i < n ? (bits[i] & 1u) : 0u); if (rem & 0x1000000u) rem ^= 0x1800063u; }
-    return rem & 0xFFFFFFu;
+    // calc_crc (liblte_phy.cc:9713-9743) ORs the whole byte into the register: the filler bits in front of the first code block are
+    // TX_NULL_SYMB = 100, not 0, and the reference's parity bits of that block depend on it -- kept, bit for bit
+    for (uint32 i = 0; i < n + 24; i++) { rem = (rem << 1) | (i < n ? (uint32)bits[i] : 0u); if (rem & 0x1000000u) rem ^= 0x1800063u; }
+    return rem;
 }
 struct SegGeom { uint32 L, C, F, Kp, Km, Cp, Cm; };
 static SegGeom seg_geom(uint32 B)

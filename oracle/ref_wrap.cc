@@ -70,6 +70,18 @@ int  ref_phy_update_n_rb_dl(void *h, int N_rb_dl) { return (int)liblte_phy_updat
 unsigned long ref_sizeof_phy_struct(void) { return sizeof(LIBLTE_PHY_STRUCT); }
 unsigned long ref_sizeof_subframe_struct(void) { return sizeof(LIBLTE_PHY_SUBFRAME_STRUCT); }
 
+/* ------------------------------------------------- code block (de)segmentation */
+/* liblte_phy.cc:9753-9865 / 9875-9987, called exactly as declared (liblte_phy.h:1337-1362) */
+void ref_code_block_segmentation(const uint8 *b_bits, unsigned N_b_bits, unsigned *N_codeblocks, unsigned *N_filler_bits, uint8 *c_bits,
+                                 unsigned N_c_bits_max, unsigned *N_c_bits)
+{
+    liblte_phy_code_block_segmentation((uint8 *)b_bits, N_b_bits, N_codeblocks, N_filler_bits, c_bits, N_c_bits_max, N_c_bits);
+}
+void ref_code_block_desegmentation(const uint8 *c_bits, unsigned *N_c_bits, unsigned N_c_bits_max, unsigned tbs, uint8 *b_bits, unsigned N_b_bits)
+{
+    liblte_phy_code_block_desegmentation((uint8 *)c_bits, N_c_bits, N_c_bits_max, tbs, b_bits, N_b_bits);
+}
+
 /* ------------------------------------------------------------------- turbo */
 /* d_out: branch-major d[x*(K+4)+i], 3*(K+4) bytes (liblte_phy.cc:10571-10586) */
 int ref_turbo_encode(void *h, const uint8 *c_bits, int K, uint8 *d_out)
