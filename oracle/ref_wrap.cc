@@ -70,6 +70,16 @@ int  ref_phy_update_n_rb_dl(void *h, int N_rb_dl) { return (int)liblte_phy_updat
 unsigned long ref_sizeof_phy_struct(void) { return sizeof(LIBLTE_PHY_STRUCT); }
 unsigned long ref_sizeof_subframe_struct(void) { return sizeof(LIBLTE_PHY_SUBFRAME_STRUCT); }
 
+/* liblte_phy_update_n_rb_dl (liblte_phy.cc:2592-2652) on a blank struct with the given samples per symbol: out = {error code, N_rb_dl, FFT_size, FFT_pad_size} */
+void ref_update_n_rb_dl_probe(unsigned N_samps_per_symb, unsigned N_rb_dl, unsigned *out)
+{
+    LIBLTE_PHY_STRUCT *p = (LIBLTE_PHY_STRUCT *)calloc(1, sizeof(LIBLTE_PHY_STRUCT));
+    p->N_samps_per_symb = N_samps_per_symb; p->N_sc_rb_dl = 12;
+    out[0] = (unsigned)liblte_phy_update_n_rb_dl(p, N_rb_dl);
+    out[1] = p->N_rb_dl; out[2] = p->FFT_size; out[3] = p->FFT_pad_size;
+    free(p);
+}
+
 /* ------------------------------------------------- code block (de)segmentation */
 /* liblte_phy.cc:9753-9865 / 9875-9987, called exactly as declared (liblte_phy.h:1337-1362) */
 void ref_code_block_segmentation(const uint8 *b_bits, unsigned N_b_bits, unsigned *N_codeblocks, unsigned *N_filler_bits, uint8 *c_bits,

@@ -189,11 +189,12 @@ def test_dci_1a_transport_block_sizes(port):
     assert lib.dci_1a_tbs(27) == -1 and lib.dci_1a_tbs(-1) == -1
 
 
-def test_code_block_segmentation_of_the_drop_in_equals_the_reference(refo, tmp_path):
+def test_host_functions_of_the_drop_in_equal_the_reference(refo, tmp_path):
     """liblte_phy_code_block_segmentation / _desegmentation of the drop-in (host code, openlte_b200/csrc/dropin.cu) against the reference's own
     functions (liblte_phy.cc:9753-9987) on random transport blocks from one to thirteen code blocks: block count, filler count, per-block sizes
     (with the reference's "+24" quirk of the multi-block branch), every byte of the segmented blocks -- including the CRC24B of the
-    first block, which the reference computes over filler bytes of value 100 -- and the desegmented bits."""
+    first block, which the reference computes over filler bytes of value 100 -- and the desegmented bits.  Also liblte_phy_update_n_rb_dl
+    (:2592-2652) for every sample rate x bandwidth pair, legal or not."""
     import subprocess
     import pytest
     if refo is None:
@@ -233,3 +234,9 @@ def test_code_block_segmentation_of_the_drop_in_equals_the_reference(refo, tmp_p
     finally:
         os.dup2(saved, 1); os.close(devnull); os.close(saved)
     assert n_multi >= 30
+    # liblte_phy_update_n_rb_dl (liblte_phy.cc:2592-2652): legal (sample rate, bandwidth) pairs, FFT size and padding, error code
+    for n_symb in (128, 256, 512, 1024, 2048, 1536, 0):
+        for n_rb in (0, 6, 10, 15, 25, 50, 75, 100, 110):
+            a = np.zeros(4, np.uint32); b = np.zeros(4, np.uint32)
+            rl.ref_update_n_rb_dl_probe(C.c_uint(n_symb), C.c_uint(n_rb), p(a)); sh.shim_update_n_rb_dl_probe(C.c_uint(n_symb), C.c_uint(n_rb), p(b))
+            assert np.array_equal(a, b), (n_symb, n_rb, a, b)
