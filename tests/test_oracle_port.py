@@ -266,3 +266,48 @@ def test_cell_search_against_live_reference(port, refo):
         err, ss3_r, nid1_r, fsi_r = phy.find_sss(i_s, q_s, nid2_r, ss2_r, th_r)
         rc, ss_s, nid1_p, fsi_p = port.find_sss(i_s, q_s, fsi_, nrb, nid2_p, ss_p, th_p)
         assert rc == err == 0 and nid1_p == nid1_r == nid1 and fsi_p == fsi_r and np.array_equal(ss_s, ss3_r), tag
+
+
+def fs_probe():
+    """oracle/_ref/libfs_probe.so: the reference's own file-scan block (fs.cc compiled unmodified) with handles on two private helpers"""
+    import ctypes as C
+    path = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "libfs_probe.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libfs_probe.so not built here (needs /root/reference)")
+    return C.CDLL(path)
+
+
+def test_freq_shift_and_capture_format_against_the_reference_block(port):
+    """LTE_fdd_dl_fs_samp_buf::freq_shift (fs.cc:696-713), the reference's own object code: the port's restatement is BIT-identical for
+    every sample rate, positive / negative / zero offsets and windows inside a larger buffer (sample numbering from the buffer start, float
+    product (i+1)*f promoted to double by M_PI).  And copy_input_to_samp_buf (fs.cc:657-694): an int8 capture is I, Q, I, Q ... as floats,
+    also when a chunk ends between an I and its Q -- the format the library's int8 loader (ofdm.cu) assumes."""
+    import ctypes as C
+    lib = fs_probe()
+    rng = np.random.default_rng(696)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for fs in (30720000, 15360000, 7680000, 3840000, 1920000):
+        for f in (0.0, 1234.5, -733.25, 7499.0, -15000.0, 3.0e-3):
+            n = int(rng.integers(2000, 70000)); start = int(rng.integers(0, n // 3)); num = int(rng.integers(1, n - start))
+            i0 = (rng.standard_normal(n) * 50).astype(np.float32); q0 = (rng.standard_normal(n) * 50).astype(np.float32)
+            ir, qr = i0.copy(), q0.copy()
+            lib.fs_probe_freq_shift(p(ir), p(qr), C.c_uint(start), C.c_uint(num), C.c_float(f), C.c_uint(fs))
+            ip, qp = port.freq_shift(i0, q0, start, num, f, fs)
+            assert np.array_equal(ip, ir) and np.array_equal(qp, qr), (fs, f, n, start, num)
+            assert np.array_equal(ir[:start], i0[:start]) and np.array_equal(qr[start + num:], q0[start + num:])
+    # large sample indices (the scan shifts up to 10 frames = 3,072,000 samples at once, fs.cc:296): the float product (i+1)*f loses integer precision there
+    n = 3_100_000
+    i0 = rng.standard_normal(n).astype(np.float32); q0 = rng.standard_normal(n).astype(np.float32)
+    ir, qr = i0.copy(), q0.copy()
+    lib.fs_probe_freq_shift(p(ir), p(qr), C.c_uint(0), C.c_uint(n), C.c_float(5321.7), C.c_uint(30720000))
+    ip, qp = port.freq_shift(i0, q0, 0, n, 5321.7, 30720000)
+    assert np.array_equal(ip, ir) and np.array_equal(qp, qr)
+    # capture format
+    items = rng.integers(-128, 128, 20001).astype(np.int8)
+    for chunks in ([20001], [7, 1, 2, 9990, 10001], [1] * 9 + [19992], [4096, 4095, 4097, 7713]):
+        assert sum(chunks) == items.size
+        cs = np.array(chunks, np.int32)
+        oi = np.zeros(items.size, np.float32); oq = np.zeros(items.size, np.float32)
+        n_c = lib.fs_probe_copy_input_int8(p(items), p(cs), len(chunks), p(oi), p(oq), items.size)
+        assert n_c == items.size // 2
+        assert np.array_equal(oi[:n_c], items[0:2 * n_c:2].astype(np.float32)) and np.array_equal(oq[:n_c], items[1:2 * n_c:2].astype(np.float32)), chunks
