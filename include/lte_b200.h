@@ -306,6 +306,15 @@ typedef struct {
     int32_t mcs[8];                      /* MCS field of each allocation's DCI */
 } lteb200_tx_control;
 int lteb200_dci_1a_tbs(int mcs);         /* 36.213 table 7.1.7.2.1-1, column N_PRB = 3 (what DCI 1A with an SI/P/RA-RNTI implies), -1 if mcs > 26 */
+/* HOST, no device needed: the channel-coded control messages as the transmitter places them, for inspection and CPU tests.
+ *   lteb200_dci_1a_encode: DCI format 1A of one allocation (contiguous PRBs from alloc->prb[0][0], alloc->rnti, alloc->rv_idx, MCS field mcs; HARQ process 0,
+ *       localized VRBs -- dci_1a_pack, liblte_phy.cc:13153-13250) + CRC16 masked with the RNTI, tail-biting convolutional code and rate matching to the
+ *       288 bits of aggregation level 4 (dci_channel_encode, :12882-12942).  Returns the transport block size the receiver will derive for an
+ *       SI/P/RA-RNTI, -1 for other RNTIs (coded all the same) and for arguments the format cannot carry.
+ *   lteb200_bch_encode: 24 MIB bits -> CRC16 with the antenna mask, convolutional code, rate matching to 1920 bits (bch_channel_encode, :12510-12571)
+ *       and scrambling with the cell's Gold sequence (liblte_phy_bch_channel_encode, :3894-3899). */
+int lteb200_dci_1a_encode(const lteb200_alloc *alloc, int mcs, int N_rb_dl, uint8_t *e288);
+int lteb200_bch_encode(const uint8_t *mib24, int N_ant, int N_id_cell, uint8_t *out1920);
 int lteb200_dl_transmit_frames_batch(lteb200_ctx *ctx, const uint8_t *d_tb_bits, int tb_stride, const lteb200_alloc *allocs, int n_alloc, int fs_idx,
                                      int N_rb_dl, const lteb200_tx_control *ctl, const int *subfr_num, int n_sf, int N_pdcch_symbs, float *d_grid,
                                      float *d_iq, void *stream);

@@ -897,6 +897,12 @@ static int dci_1a_encode_host(const lteb200_alloc &al, int mcs, int N_rb_dl, uin
     return common ? kTbsNprb3[mcs] : -1;                 // the reference's receiver handles SI/P/RA-RNTI only (dci_1a_unpack, :13273)
 }
 extern "C" int lteb200_dci_1a_tbs(int mcs) { return (mcs >= 0 && mcs <= 26) ? kTbsNprb3[mcs] : -1; }
+// HOST, no device needed: the coded DCI as the transmitter places it (for inspection and CPU tests)
+extern "C" int lteb200_dci_1a_encode(const lteb200_alloc *alloc, int mcs, int N_rb_dl, uint8_t *e288)
+{
+    if (!alloc || !e288 || N_rb_dl < 6 || N_rb_dl > 110) return -1;
+    return dci_1a_encode_host(*alloc, mcs, N_rb_dl, e288);
+}
 
 // 24 MIB bits -> 1920 coded, rate matched and scrambled bits (4 x 480: one row per radio frame of the 40 ms period)
 static void bch_encode_host(const uint8_t *mib24, int N_ant, int N_id_cell, uint8_t *out1920)
@@ -911,6 +917,14 @@ static void bch_encode_host(const uint8_t *mib24, int N_ant, int N_id_cell, uint
     std::vector<uint8_t> s(1920);
     prs_c_host((uint32_t)N_id_cell, 1920, s.data());
     for (int i = 0; i < 1920; i++) out1920[i] ^= s[i];
+}
+
+// HOST, no device needed
+extern "C" int lteb200_bch_encode(const uint8_t *mib24, int N_ant, int N_id_cell, uint8_t *out1920)
+{
+    if (!mib24 || !out1920 || !(N_ant == 1 || N_ant == 2 || N_ant == 4) || N_id_cell < 0 || N_id_cell > 503) return LTEB200_ERR_ARGS;
+    bch_encode_host(mib24, N_ant, N_id_cell, out1920);
+    return LTEB200_OK;
 }
 
 void gen_pss(int N_id_2, float2 *out);                                   // sync.cu (generate_pss / generate_sss twins)

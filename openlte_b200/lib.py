@@ -101,6 +101,8 @@ SYMBOLS = {
     "lteb200_pdsch_llr_q8_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_turbo_decode_q8_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "lteb200_dci_1a_tbs": (_i, [_i]),
+    "lteb200_dci_1a_encode": (_i, [_vp, _i, _i, _vp]),
+    "lteb200_bch_encode": (_i, [_vp, _i, _i, _vp]),
     "lteb200_dl_transmit_frames_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "lteb200_dl_transmit_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "lteb200_freq_shift_batch": (_i, [_vp, _vp, _i, _ll, _ll, _f, _i, _vp, _vp]),

@@ -51,6 +51,9 @@ void viterbi_decode(LIBLTE_PHY_STRUCT *, float *, uint32, uint32, uint32, uint32
 LIBLTE_ERROR_ENUM dci_1a_unpack(uint8 *, uint32, LIBLTE_PHY_DCI_CA_PRESENCE_ENUM, uint16, uint32, uint8,
                                 LIBLTE_PHY_ALLOCATION_STRUCT *);                                           /* :2021 */
 LIBLTE_ERROR_ENUM dci_1c_unpack(uint8 *, uint32, uint16, uint32, uint8, LIBLTE_PHY_ALLOCATION_STRUCT *);    /* :2061 */
+void dci_1a_pack(LIBLTE_PHY_ALLOCATION_STRUCT *, LIBLTE_PHY_DCI_CA_PRESENCE_ENUM, uint32, uint8, uint8 *, uint32 *);   /* :1997 */
+void dci_channel_encode(LIBLTE_PHY_STRUCT *, uint8 *, uint32, uint16, uint8, uint32, uint8 *);                          /* :1905 */
+void bch_channel_encode(LIBLTE_PHY_STRUCT *, uint8 *, uint32, uint8, uint8 *, uint32 *);                                /* :1821 */
 extern uint32 TBS_71721[27][110];                                                                          /* :477 */
 extern uint32 TBS_71723[32];                                                                               /* :749 */
 
@@ -69,6 +72,30 @@ void ref_phy_cleanup(void *h) { if (h) liblte_phy_cleanup((LIBLTE_PHY_STRUCT *)h
 int  ref_phy_update_n_rb_dl(void *h, int N_rb_dl) { return (int)liblte_phy_update_n_rb_dl((LIBLTE_PHY_STRUCT *)h, N_rb_dl); }
 unsigned long ref_sizeof_phy_struct(void) { return sizeof(LIBLTE_PHY_STRUCT); }
 unsigned long ref_sizeof_subframe_struct(void) { return sizeof(LIBLTE_PHY_SUBFRAME_STRUCT); }
+
+/* ---------------------------------------------------------- transmit-side channel coding */
+/* dci_1a_pack (liblte_phy.cc:13153-13250) + dci_channel_encode (:12882-12942) at aggregation level 4 (288 bits), as
+ * liblte_phy_pdcch_channel_encode calls them (:4301-4316).  Returns the payload size; *tbs = what dci_1a_pack stored in the allocation. */
+int ref_dci_1a_encode(void *h, int rnti, int mcs, int N_prb, int prb0, int rv_idx, int N_rb_dl, uint8 *out288, int *tbs)
+{
+    LIBLTE_PHY_ALLOCATION_STRUCT a;
+    memset(&a, 0, sizeof(a));
+    a.rnti = (uint16)rnti; a.mcs = (uint8)mcs; a.N_prb = (uint32)N_prb; a.rv_idx = (uint32)rv_idx;
+    for (int j = 0; j < N_prb && j < 110; j++) { a.prb[0][j] = prb0 + j; a.prb[1][j] = prb0 + j; }
+    uint8 bits[128];
+    uint32 n = 0;
+    dci_1a_pack(&a, LIBLTE_PHY_DCI_CA_NOT_PRESENT, (uint32)N_rb_dl, 1, bits, &n);
+    dci_channel_encode((LIBLTE_PHY_STRUCT *)h, bits, n, (uint16)rnti, 0, 288, out288);
+    *tbs = (int)a.tbs;
+    return (int)n;
+}
+/* bch_channel_encode (liblte_phy.cc:12510-12571): 24 MIB bits -> 1920 coded bits, BEFORE the scrambling of liblte_phy_bch_channel_encode (:3894-3899) */
+int ref_bch_encode_bits(void *h, const uint8 *mib24, int N_ant, uint8 *out1920)
+{
+    uint32 n = 0;
+    bch_channel_encode((LIBLTE_PHY_STRUCT *)h, (uint8 *)mib24, 24, (uint8)N_ant, out1920, &n);
+    return (int)n;
+}
 
 /* liblte_phy_update_n_rb_dl (liblte_phy.cc:2592-2652) on a blank struct with the given samples per symbol: out = {error code, N_rb_dl, FFT_size, FFT_pad_size} */
 void ref_update_n_rb_dl_probe(unsigned N_samps_per_symb, unsigned N_rb_dl, unsigned *out)

@@ -240,3 +240,47 @@ def test_host_functions_of_the_drop_in_equal_the_reference(refo, tmp_path):
             a = np.zeros(4, np.uint32); b = np.zeros(4, np.uint32)
             rl.ref_update_n_rb_dl_probe(C.c_uint(n_symb), C.c_uint(n_rb), p(a)); sh.shim_update_n_rb_dl_probe(C.c_uint(n_symb), C.c_uint(n_rb), p(b))
             assert np.array_equal(a, b), (n_symb, n_rb, a, b)
+
+
+def test_transmit_side_channel_coding_equals_the_reference(refo, port):
+    """Host code of the device transmitter against the reference's own functions on random inputs: DCI format 1A packing + channel coding to 288
+    bits (dci_1a_pack liblte_phy.cc:13153-13250, dci_channel_encode :12882-12942) for every bandwidth, allocation size / position, MCS,
+    redundancy version and the SI / P / RA RNTIs, with the transport block size the packer derives; and the PBCH coding chain (bch_channel_encode
+    :12510-12571 + the scrambling of :3894-3899) for 1 / 2 / 4 ports."""
+    import pytest
+    if refo is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    lib = openlte_b200.load(); rl = refo.lib(); phy = refo.RefPhy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(1353)
+    n = 0
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
+    try:
+        for n_rb in (6, 15, 25, 50, 75, 100):
+            for trial in range(60):
+                n_prb = int(rng.integers(1, n_rb + 1)); prb0 = int(rng.integers(0, n_rb - n_prb + 1))
+                mcs = int(rng.integers(0, 27)); rv = int(rng.integers(0, 4))
+                rnti = int(rng.choice([0xFFFF, 0xFFFE, int(rng.integers(1, 0x3D))]))
+                al = Alloc.make(1, list(range(prb0, prb0 + n_prb)), 0, rnti, rv_idx=rv)
+                got = np.zeros(288, np.uint8); want = np.zeros(288, np.uint8); tbs_ref = C.c_int(0)
+                tbs = lib.dci_1a_encode(C.byref(al), mcs, n_rb, p(got))
+                rl.ref_dci_1a_encode(phy.h, rnti, mcs, n_prb, prb0, rv, n_rb, p(want), C.byref(tbs_ref))
+                assert np.array_equal(got, want), (n_rb, n_prb, prb0, mcs, rv, hex(rnti))
+                assert tbs == tbs_ref.value == lib.dci_1a_tbs(mcs)
+                n += 1
+    finally:
+        os.dup2(saved, 1); os.close(devnull); os.close(saved)
+    assert n == 360
+    # refusals: non-contiguous PRBs, MCS beyond the table
+    al = Alloc.make(1, [3, 5], 0, 0xFFFF); out = np.zeros(288, np.uint8)
+    assert lib.dci_1a_encode(C.byref(al), 3, 25, p(out)) == -1
+    al = Alloc.make(1, [3, 4], 0, 0xFFFF)
+    assert lib.dci_1a_encode(C.byref(al), 27, 25, p(out)) == -1
+    # PBCH
+    for trial in range(30):
+        mib = rng.integers(0, 2, 24).astype(np.uint8); n_ant = (1, 2, 4)[trial % 3]; cell = int(rng.integers(0, 504))
+        got = np.zeros(1920, np.uint8); coded = np.zeros(1920, np.uint8)
+        assert lib.bch_encode(p(mib), n_ant, cell, p(got)) == 0
+        assert rl.ref_bch_encode_bits(phy.h, p(mib), n_ant, p(coded)) == 1920
+        assert np.array_equal(got, coded ^ port.prs_c(cell, 1920)), (n_ant, cell)
+    assert lib.bch_encode(p(mib), 3, 0, p(got)) == -1
