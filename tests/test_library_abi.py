@@ -62,3 +62,22 @@ def test_product_does_not_reference_the_oracle():
                     assert "liboracle" not in code and "libref_oracle" not in code and "from oracle" not in code and "import oracle" not in code, os.path.join(dp, fn)
     out = subprocess.run(["ldd", os.path.join(ROOT, "openlte_b200", "libopenlte_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_standalone_drop_in_header_has_the_reference_layout(tmp_path):
+    """include/liblte_phy_b200.h in its self-contained mode (no reference headers on the include path) against the reference's own liblte_phy.h:
+    error / sample-rate / modulation / channel-type / pre-coder enum values, sizes of the subframe, allocation, coarse-timing, PDCCH, PCFICH, PHICH
+    and bit-message structs and the offsets of every field the path reads or writes -- a caller compiled against either header passes the same bytes."""
+    import subprocess
+    import pytest
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "liblte", "hdr")):
+        pytest.skip("needs the reference headers (/root/reference)")
+    src = os.path.join(ROOT, "tests", "cpp", "layout_probe.cc")
+    a, b = str(tmp_path / "ref"), str(tmp_path / "b200")
+    subprocess.run(["g++", "-fsigned-char", "-DUSE_REF", "-I", os.path.join(ref, "liblte", "hdr"), "-I", os.path.join(ref, "cmn_hdr"), "-I", os.path.join(ROOT, "oracle", "fftw3_shim"),
+                    src, "-o", a], check=True, capture_output=True)
+    subprocess.run(["g++", "-DLIBLTE_PHY_B200_STANDALONE", "-I", os.path.join(ROOT, "include"), src, "-o", b], check=True, capture_output=True)
+    ra = subprocess.run([a], capture_output=True, text=True, check=True).stdout
+    rb = subprocess.run([b], capture_output=True, text=True, check=True).stdout
+    assert ra == rb and "SUBFRAME 1382404" in ra, (ra, rb)
